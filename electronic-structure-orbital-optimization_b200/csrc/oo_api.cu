@@ -1,0 +1,784 @@
+// liboo_b200.so — C ABI (include/oo_b200.h) over the sm_100a kernels.
+// Host side only orchestrates: context, workspaces, TMA descriptor, launches, NCCL (dlopen'ed).
+#include "../../include/oo_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "oo_bench.cuh"
+#include "oo_common.cuh"
+#include "oo_ingest.cuh"
+#include "oo_k1.cuh"
+#include "oo_k2.cuh"
+#include "oo_k3.cuh"
+
+using namespace oo;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(OO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so the library loads on machines without it
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId128 {
+  char internal[128];
+};
+typedef int (*nccl_get_unique_id_t)(NcclUniqueId128*);
+typedef int (*nccl_comm_init_rank_t)(void**, int, NcclUniqueId128, int);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_comm_destroy_t)(void*);
+typedef const char* (*nccl_get_error_string_t)(int);
+constexpr int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64
+constexpr int kNcclSum = 0;      // ncclRedOp_t::ncclSum
+
+struct NcclApi {
+  void* handle = nullptr;
+  nccl_get_unique_id_t get_unique_id = nullptr;
+  nccl_comm_init_rank_t comm_init_rank = nullptr;
+  nccl_all_reduce_t all_reduce = nullptr;
+  nccl_comm_destroy_t comm_destroy = nullptr;
+  nccl_get_error_string_t get_error_string = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return OO_OK;
+  const char* cand[] = {getenv("OO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* c : cand) {
+    if (!c || !*c) continue;
+    h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(OO_ERR_NCCL, "cannot dlopen libnccl.so.2 (set OO_NCCL_LIB): %s", dlerror());
+  NcclApi a;
+  a.handle = h;
+  a.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
+  a.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+  a.all_reduce = (nccl_all_reduce_t)dlsym(h, "ncclAllReduce");
+  a.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+  a.get_error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
+  if (!a.get_unique_id || !a.comm_init_rank || !a.all_reduce || !a.comm_destroy ||
+      !a.get_error_string)
+    return fail(OO_ERR_NCCL, "libnccl is missing a required symbol");
+  g_nccl = a;
+  return OO_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct oo_ctx {
+  int device = 0, M = 0, N = 0, NT = 0, Np = 0, t0 = 0, mloc = 0;
+  int num_sms = 0, nstage = 0, Mk = 0;
+  size_t k1_smem = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  const double* h = nullptr;
+  const double* g = nullptr;
+  unsigned gflags = 0;
+  bool have_ints = false, have_rdms = false;
+  alignas(64) CUtensorMap tmap;
+  // workspaces (device)
+  double *Y = nullptr, *T3 = nullptr, *Gp = nullptr, *D = nullptr, *A = nullptr, *UD = nullptr,
+         *UDt = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
+         *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr;
+  int hist_cap = 0;
+  unsigned int* counter = nullptr;
+  OptState* state = nullptr;
+  // pinned host staging
+  double* pin = nullptr;        // M*N+1 doubles
+  OptState* pin_state = nullptr;  // 2 slots
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  // NCCL
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[5] = {0, 0, 0, 0, 0};
+  long long launches = 0;
+};
+
+namespace {
+
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(encode_tiled_t* fn) {
+  static encode_tiled_t cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p)
+      return fail(OO_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    cached = (encode_tiled_t)p;
+  }
+  *fn = cached;
+  return OO_OK;
+}
+
+// 3-D view of the shard: (s: M, r: M, slab: mloc*M), box 16 x 256 x 1, 128B swizzle, zero fill.
+int build_tmap(oo_ctx* c) {
+  encode_tiled_t enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const cuuint64_t dims[3] = {(cuuint64_t)c->M, (cuuint64_t)c->M, (cuuint64_t)c->mloc * c->M};
+  const cuuint64_t strides[2] = {(cuuint64_t)c->M * 8, (cuuint64_t)c->M * c->M * 8};
+  const cuuint32_t box[3] = {K1_KC, K1_ROWS, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(c->g), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OO_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return OO_OK;
+}
+
+template <int NT>
+int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag) {
+  K1Params p;
+  p.U = U;
+  p.Y = c->Y;
+  p.done_flag = done_flag;
+  p.M = c->M;
+  p.N = c->N;
+  p.nslab = c->mloc * c->M;
+  p.nstage = c->nstage;
+  p.Mk = c->Mk;
+  p.upitch = c->Mk + 8;
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[c->device & 7]) {
+    CU_TRY(cudaFuncSetAttribute(k1_half_transform<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                227 * 1024));
+    attr_set[c->device & 7] = true;
+  }
+  const int grid = std::min(c->num_sms, p.nslab);
+  k1_half_transform<NT><<<grid, K1_THREADS, c->k1_smem, c->stream>>>(c->tmap, p);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int launch_k1(oo_ctx* c, const double* U, const int* done_flag) {
+  switch (c->NT) {
+    case 1: return launch_k1_t<1>(c, U, done_flag);
+    case 2: return launch_k1_t<2>(c, U, done_flag);
+    case 3: return launch_k1_t<3>(c, U, done_flag);
+    case 4: return launch_k1_t<4>(c, U, done_flag);
+  }
+  return fail(OO_ERR_INVALID, "unsupported N");
+}
+
+template <int NT>
+int launch_qc_t(oo_ctx* c, const double* U, const int* done_flag) {
+  constexpr int Np = NT * 8;
+  const size_t smem = ((size_t)c->M * Np + (size_t)QC_QGROUPS * Np * QC_ECHUNK) * sizeof(double);
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[c->device & 7]) {
+    CU_TRY(cudaFuncSetAttribute(k_qcontract<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                227 * 1024));
+    attr_set[c->device & 7] = true;
+  }
+  if (smem > 227 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
+  dim3 grid(c->mloc, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
+  k_qcontract<NT><<<grid, QC_ECHUNK * QC_QGROUPS, smem, c->stream>>>(c->Y, U, c->T3, c->M, c->N,
+                                                                    done_flag);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int launch_qc(oo_ctx* c, const double* U, const int* done_flag) {
+  switch (c->NT) {
+    case 1: return launch_qc_t<1>(c, U, done_flag);
+    case 2: return launch_qc_t<2>(c, U, done_flag);
+    case 3: return launch_qc_t<3>(c, U, done_flag);
+    case 4: return launch_qc_t<4>(c, U, done_flag);
+  }
+  return fail(OO_ERR_INVALID, "unsupported N");
+}
+
+// One evaluation: shard rows of dE/dU and partial E into `out` (device, M*N+1).
+int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) {
+  if (!c->have_ints) return fail(OO_ERR_STATE, "oo_set_integrals has not been called");
+  if (!c->have_rdms) return fail(OO_ERR_STATE, "oo_set_rdms has not been called");
+  const bool tm = c->timing;
+  int rc;
+  if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = launch_k1(c, U, done_flag))) return rc;
+  if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
+  if ((rc = launch_qc(c, U, done_flag))) return rc;
+  if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+  {
+    const int L = c->Np * c->Np * c->Np;
+    dim3 grid(c->mloc, (c->N + GC_AGROUP - 1) / GC_AGROUP);
+    k_gamma_contract<<<grid, 256, 0, c->stream>>>(c->T3, c->Gp, c->A, c->N, L, done_flag);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
+  {
+    k_ud<<<c->M, 32, 0, c->stream>>>(U, c->D, c->UD, c->UDt, c->N, done_flag);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    FinalizeParams fp;
+    fp.h = c->h;
+    fp.U = U;
+    fp.UD = c->UD;
+    fp.UDt = c->UDt;
+    fp.A = c->A;
+    fp.out = out;
+    fp.rowE = c->rowE;
+    fp.counter = c->counter;
+    fp.done_flag = done_flag;
+    fp.M = c->M;
+    fp.N = c->N;
+    fp.t0 = c->t0;
+    fp.Mloc = c->mloc;
+    fp.two_body_grad_factor = 4.0;
+    k_finalize<<<c->mloc, 128, 0, c->stream>>>(fp);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  if (tm) CU_TRY(cudaEventRecord(c->ev[4], c->stream));
+  return OO_OK;
+}
+
+int do_allreduce(oo_ctx* c, double* buf, size_t count) {
+  if (!c->comm) return OO_OK;
+  int r = g_nccl.all_reduce(buf, buf, count, kNcclFloat64, kNcclSum, c->comm, c->stream);
+  if (r != 0) return fail(OO_ERR_NCCL, "ncclAllReduce: %s", g_nccl.get_error_string(r));
+  return OO_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* oo_last_error(void) { return g_last_error.c_str(); }
+const char* oo_version(void) { return "oo_b200 0.1 (sm_100a)"; }
+
+int oo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OO_ERR_CUDA, "no CUDA device visible");
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
+  if (!out) return fail(OO_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (M < 1 || N < 1 || N > M) return fail(OO_ERR_INVALID, "need 1 <= N <= M (got M=%d N=%d)", M, N);
+  if (N > K3_NMAX) return fail(OO_ERR_UNSUPPORTED, "N=%d > %d is not supported", N, K3_NMAX);
+  if (M % 2) return fail(OO_ERR_UNSUPPORTED, "M must be even (pad the integrals); got %d", M);
+  if (t0 < 0 || mloc < 1 || t0 + mloc > M)
+    return fail(OO_ERR_INVALID, "bad shard [%d,%d) for M=%d", t0, t0 + mloc, M);
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(OO_ERR_INVALID, "device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(OO_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
+                prop.major, prop.minor);
+  CU_TRY(cudaSetDevice(device));
+  oo_ctx* c = new oo_ctx();
+  c->device = device;
+  c->M = M;
+  c->N = N;
+  c->NT = (N + 7) / 8;
+  c->Np = c->NT * 8;
+  c->t0 = t0;
+  c->mloc = mloc;
+  c->num_sms = prop.multiProcessorCount;
+  c->Mk = (M + K1_KC - 1) / K1_KC * K1_KC;
+  // deepest TMA ring that fits 227 KiB
+  c->nstage = 0;
+  for (int ns = 6; ns >= 2; --ns) {
+    if (k1_smem_bytes(c->NT, c->Mk, ns) <= (size_t)227 * 1024) {
+      c->nstage = ns;
+      break;
+    }
+  }
+  if (!c->nstage) {
+    delete c;
+    return fail(OO_ERR_UNSUPPORTED, "M=%d N=%d does not fit the K1 shared-memory plan", M, N);
+  }
+  c->k1_smem = k1_smem_bytes(c->NT, c->Mk, c->nstage);
+  const size_t MN = (size_t)M * N, Np2 = (size_t)c->Np * c->Np;
+  auto alloc = [&](double** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(double)); };
+  cudaError_t e = cudaSuccess;
+  auto A = [&](double** p, size_t n) {
+    if (e == cudaSuccess) e = alloc(p, n);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(double));
+  };
+  A(&c->Y, (size_t)mloc * M * Np2);
+  A(&c->T3, (size_t)mloc * c->Np * Np2);
+  A(&c->Gp, (size_t)N * c->Np * Np2);
+  A(&c->D, (size_t)N * N);
+  A(&c->A, (size_t)mloc * N);
+  A(&c->UD, MN);
+  A(&c->UDt, MN);
+  A(&c->rowE, mloc);
+  A(&c->out, MN + 1);
+  A(&c->Ucur, MN);
+  A(&c->Uprev, MN);
+  A(&c->Gprev, MN);
+  A(&c->Vtmp, MN);
+  A(&c->alpha_tmp, 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->counter, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(c->counter, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->state, sizeof(OptState));
+  if (e == cudaSuccess) e = cudaMemset(c->state, 0, sizeof(OptState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin, (MN + 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin_state, 2 * sizeof(OptState));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+    e = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    int rc = fail(OO_ERR_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    oo_destroy(c);
+    return rc;
+  }
+  c->own_stream = true;
+  *out = c;
+  return OO_OK;
+}
+
+int oo_destroy(oo_ctx* c) {
+  if (!c) return OO_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
+  double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
+                    c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp};
+  for (double* b : bufs)
+    if (b) cudaFree(b);
+  if (c->counter) cudaFree(c->counter);
+  if (c->state) cudaFree(c->state);
+  if (c->pin) cudaFreeHost(c->pin);
+  if (c->pin_state) cudaFreeHost(c->pin_state);
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->poll_ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return OO_OK;
+}
+
+int oo_set_stream(oo_ctx* c, void* cuda_stream) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  CU_TRY(cudaSetDevice(c->device));
+  if (c->own_stream && c->stream) {
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaStreamDestroy(c->stream));
+    c->own_stream = false;
+  }
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+  } else {
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return OO_OK;
+}
+
+int oo_synchronize(oo_ctx* c) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return OO_OK;
+}
+
+int oo_set_integrals(oo_ctx* c, const double* h_dev, const double* g_dev, unsigned flags) {
+  if (!c || !h_dev || !g_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  if (((uintptr_t)g_dev & 15) != 0) return fail(OO_ERR_INVALID, "g must be 16-byte aligned");
+  if (!(flags & OO_G_V4_SYMMETRIC))
+    return fail(OO_ERR_UNSUPPORTED,
+                "only V4-symmetric two-body tensors (g[pqrs]=g[qpsr]=g[rspq]) are supported; "
+                "verify with oo_check_v4_symmetry and pass OO_G_V4_SYMMETRIC");
+  CU_TRY(cudaSetDevice(c->device));
+  c->h = h_dev;
+  c->g = g_dev;
+  c->gflags = flags;
+  int rc = build_tmap(c);
+  if (rc) return rc;
+  c->have_ints = true;
+  return OO_OK;
+}
+
+int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_host) {
+  if (!g_dev || !out_host || M < 1) return fail(OO_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CU_TRY(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+  CU_TRY(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  k_v4_symmetry<<<148 * 8, 256>>>(g_dev, M, d);
+  cudaError_t e = cudaGetLastError();
+  unsigned long long hbits[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(hbits, d, sizeof hbits, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(OO_ERR_CUDA, "symmetry check: %s", cudaGetErrorString(e));
+  memcpy(out_host, hbits, sizeof hbits);
+  return OO_OK;
+}
+
+int oo_set_rdms(oo_ctx* c, const double* D_dev, const double* G_dev) {
+  if (!c || !D_dev || !G_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMemcpyAsync(c->D, D_dev, (size_t)c->N * c->N * sizeof(double),
+                         cudaMemcpyDeviceToDevice, c->stream));
+  k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp, c->N, c->Np, 1);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  c->have_rdms = true;
+  return OO_OK;
+}
+
+int oo_energy_grad(oo_ctx* c, const double* U_dev, double* out_dev) {
+  if (!c || !U_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  return enqueue_eval(c, U_dev, out_dev ? out_dev : c->out, nullptr);
+}
+
+int oo_energy_grad_host(oo_ctx* c, const double* U_host, double* E_host, double* grad_host) {
+  if (!c || !U_host || !E_host) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t MN = (size_t)c->M * c->N;
+  memcpy(c->pin, U_host, MN * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(c->Ucur, c->pin, MN * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int rc = enqueue_eval(c, c->Ucur, c->out, nullptr);
+  if (rc) return rc;
+  if ((rc = do_allreduce(c, c->out, MN + 1))) return rc;
+  CU_TRY(cudaMemcpyAsync(c->pin, c->out, (MN + 1) * sizeof(double), cudaMemcpyDeviceToHost,
+                         c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  *E_host = c->pin[MN];
+  if (grad_host) memcpy(grad_host, c->pin, MN * sizeof(double));
+  return OO_OK;
+}
+
+int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_rot_dev) {
+  if (!c || !U_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  if (!c->have_ints) return fail(OO_ERR_STATE, "oo_set_integrals has not been called");
+  CU_TRY(cudaSetDevice(c->device));
+  int rc;
+  if (g_rot_dev) {
+    if ((rc = launch_k1(c, U_dev, nullptr))) return rc;
+    if ((rc = launch_qc(c, U_dev, nullptr))) return rc;
+    k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np, c->t0,
+                                                   c->mloc);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  if (h_rot_dev) {
+    k_rotate_h<<<c->N * c->N, 128, 0, c->stream>>>(c->h, U_dev, h_rot_dev, c->M, c->N, c->t0,
+                                                   c->mloc);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return OO_OK;
+}
+
+int oo_orth(oo_ctx* c, const double* V_dev, double* U_out_dev) {
+  if (!c || !V_dev || !U_out_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  k_orth<<<1, K3_THREADS, 0, c->stream>>>(V_dev, U_out_dev, c->M, c->N);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int oo_bb_update(oo_ctx* c, int iteration, const double* U_cur_dev, const double* U_prev_dev,
+                 const double* G_cur_dev, const double* G_prev_dev, double* alpha_io_dev,
+                 double* U_new_dev) {
+  if (!c || !U_cur_dev || !G_cur_dev || !alpha_io_dev || !U_new_dev)
+    return fail(OO_ERR_INVALID, "NULL argument");
+  if (iteration >= 1 && (!U_prev_dev || !G_prev_dev))
+    return fail(OO_ERR_INVALID, "previous iterates are required for iteration >= 1");
+  CU_TRY(cudaSetDevice(c->device));
+  BBParams p;
+  p.Ucur = U_cur_dev;
+  p.Uprev = U_prev_dev;
+  p.Gcur = G_cur_dev;
+  p.Gprev = G_prev_dev;
+  p.Unew = U_new_dev;
+  p.Vtmp = c->Vtmp;
+  p.alpha_io = alpha_io_dev;
+  p.iteration = iteration;
+  p.M = c->M;
+  p.N = c->N;
+  k_bb_update<<<1, K3_THREADS, 0, c->stream>>>(p);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxiter, double decay,
+                double* E_hist_host, int hist_cap, int* n_iter, double* E_final,
+                double* bb_final) {
+  if (!c || !U_io_host) return fail(OO_ERR_INVALID, "NULL argument");
+  if (!c->have_ints || !c->have_rdms) return fail(OO_ERR_STATE, "integrals / RDMs not set");
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t MN = (size_t)c->M * c->N;
+  const int need_hist = std::max(maxiter, 0) + 8;
+  if (c->hist_cap < need_hist) {
+    if (c->E_hist) CU_TRY(cudaFree(c->E_hist));
+    c->E_hist = nullptr;
+    CU_TRY(cudaMalloc((void**)&c->E_hist, (size_t)need_hist * sizeof(double)));
+    c->hist_cap = need_hist;
+  }
+  CU_TRY(cudaMemsetAsync(c->E_hist, 0, (size_t)c->hist_cap * sizeof(double), c->stream));
+  memcpy(c->pin, U_io_host, MN * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(c->Ucur, c->pin, MN * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  OptState init;
+  memset(&init, 0, sizeof init);
+  init.alpha = bb0;
+  init.S[1] = 1.5 * tol;  // St_array = [None, 1.5*tol]  (pupo.py:178)
+  init.tol = tol;
+  init.decay = decay;
+  init.maxiter = maxiter;
+  c->pin_state[0] = init;
+  CU_TRY(cudaMemcpyAsync(c->state, &c->pin_state[0], sizeof(OptState), cudaMemcpyHostToDevice,
+                         c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));  // pin_state[0] is reused below
+
+  StepParams sp;
+  sp.st = c->state;
+  sp.Ucur = c->Ucur;
+  sp.Uprev = c->Uprev;
+  sp.gE = c->out;
+  sp.Gprev = c->Gprev;
+  sp.Vtmp = c->Vtmp;
+  sp.E_hist = c->E_hist;
+  sp.M = c->M;
+  sp.N = c->N;
+  sp.hist_cap = c->hist_cap;
+  const int* done_flag = &c->state->done;
+
+  // Transitions are enqueued in chunks; the stop flag of chunk i is inspected while chunk i+1
+  // is already queued, so the device never idles on the host.  Transitions after the stop are
+  // no-ops (every kernel tests the flag first).
+  const int chunk = 4;
+  const long max_transitions = (long)std::max(maxiter, 3) + 4;
+  long enq = 0;
+  int slot = 0;
+  bool pending[2] = {false, false};
+  bool done = false;
+  auto enqueue_chunk = [&](int s) -> int {
+    int rc;
+    for (int i = 0; i < chunk; ++i) {
+      if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag))) return rc;
+      if ((rc = do_allreduce(c, c->out, MN + 1))) return rc;
+      k_step<<<1, K3_THREADS, 0, c->stream>>>(sp);
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+      ++enq;
+    }
+    CU_TRY(cudaMemcpyAsync(&c->pin_state[s], c->state, sizeof(OptState), cudaMemcpyDeviceToHost,
+                           c->stream));
+    CU_TRY(cudaEventRecord(c->poll_ev[s], c->stream));
+    pending[s] = true;
+    return OO_OK;
+  };
+  int rc = enqueue_chunk(slot);
+  if (rc) return rc;
+  while (!done) {
+    const int other = slot ^ 1;
+    if (enq < max_transitions) {
+      if ((rc = enqueue_chunk(other))) return rc;
+    }
+    CU_TRY(cudaEventSynchronize(c->poll_ev[slot]));
+    pending[slot] = false;
+    if (c->pin_state[slot].done) {
+      done = true;
+    } else if (!pending[other]) {
+      return fail(OO_ERR_NUMERIC, "optimiser did not stop within %ld transitions", enq);
+    }
+    slot = other;
+  }
+  CU_TRY(cudaMemcpyAsync(c->pin, c->Ucur, MN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(&c->pin_state[0], c->state, sizeof(OptState), cudaMemcpyDeviceToHost,
+                         c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  const OptState fin = c->pin_state[0];
+  memcpy(U_io_host, c->pin, MN * sizeof(double));
+  if (E_hist_host && hist_cap > 0) {
+    const int n = std::min(hist_cap, c->hist_cap);
+    CU_TRY(cudaMemcpy(E_hist_host, c->E_hist, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (n_iter) *n_iter = fin.k_final;
+  if (E_final) *E_final = fin.E_final;
+  if (bb_final) *bb_final = fin.alpha;
+  if (fin.nan_flag) return fail(OO_ERR_NUMERIC, "non-finite value met during the optimisation");
+  return OO_OK;
+}
+
+int oo_nccl_unique_id(void* id128_host) {
+  if (!id128_host) return fail(OO_ERR_INVALID, "NULL argument");
+  int rc = load_nccl();
+  if (rc) return rc;
+  NcclUniqueId128 id;
+  int r = g_nccl.get_unique_id(&id);
+  if (r != 0) return fail(OO_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.get_error_string(r));
+  memcpy(id128_host, &id, sizeof id);
+  return OO_OK;
+}
+
+int oo_comm_init(oo_ctx* c, const void* id128_host, int rank, int world) {
+  if (!c || !id128_host || rank < 0 || rank >= world)
+    return fail(OO_ERR_INVALID, "bad communicator arguments");
+  int rc = load_nccl();
+  if (rc) return rc;
+  CU_TRY(cudaSetDevice(c->device));
+  NcclUniqueId128 id;
+  memcpy(&id, id128_host, sizeof id);
+  void* comm = nullptr;
+  int r = g_nccl.comm_init_rank(&comm, world, id, rank);
+  if (r != 0) return fail(OO_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.get_error_string(r));
+  c->comm = comm;
+  c->rank = rank;
+  c->world = world;
+  return OO_OK;
+}
+
+int oo_allreduce(oo_ctx* c, double* buf_dev, size_t count) {
+  if (!c || !buf_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  if (!c->comm) return fail(OO_ERR_STATE, "no communicator attached (oo_comm_init)");
+  CU_TRY(cudaSetDevice(c->device));
+  return do_allreduce(c, buf_dev, count);
+}
+
+int oo_set_timing(oo_ctx* c, int enable) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  c->timing = enable != 0;
+  return OO_OK;
+}
+
+int oo_last_timing(oo_ctx* c, float* ms5_host) {
+  if (!c || !ms5_host) return fail(OO_ERR_INVALID, "NULL argument");
+  if (!c->timing) return fail(OO_ERR_STATE, "timing is not enabled");
+  CU_TRY(cudaEventSynchronize(c->ev[4]));
+  for (int i = 0; i < 4; ++i) CU_TRY(cudaEventElapsedTime(&ms5_host[i], c->ev[i], c->ev[i + 1]));
+  CU_TRY(cudaEventElapsedTime(&ms5_host[4], c->ev[0], c->ev[4]));
+  return OO_OK;
+}
+
+long long oo_launch_count(oo_ctx* c) { return c ? c->launches : 0; }
+
+int oo_measure_peaks(int device, size_t bytes, double* out_host) {
+  if (!out_host) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  const int sms = prop.multiProcessorCount;
+  double* d = nullptr;
+  CU_TRY(cudaMalloc((void**)&d, 64));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  float ms = 0.f;
+  // DMMA: 2 CTAs/SM x 8 warps, 16 chains per warp
+  {
+    const int iters = 4096, grid = sms * 2;
+    k_peak_dmma<<<grid, 256>>>(d, 64);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+      CU_TRY(cudaEventRecord(e0));
+      k_peak_dmma<<<grid, 256>>>(d, iters);
+      CU_TRY(cudaEventRecord(e1));
+      CU_TRY(cudaEventSynchronize(e1));
+      CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = (double)grid * 8 * iters * 16 * 512.0;
+      best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    out_host[0] = best;
+  }
+  {
+    const int iters = 4096, grid = sms * 4;
+    k_peak_dfma<<<grid, 256>>>(d, 64);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+      CU_TRY(cudaEventRecord(e0));
+      k_peak_dfma<<<grid, 256>>>(d, iters);
+      CU_TRY(cudaEventRecord(e1));
+      CU_TRY(cudaEventSynchronize(e1));
+      CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      const double fl = (double)grid * 256 * iters * 16 * 2.0;
+      best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    out_host[1] = best;
+  }
+  {
+    if (bytes < (size_t)1 << 20) bytes = (size_t)1 << 20;
+    double2* buf = nullptr;
+    CU_TRY(cudaMalloc((void**)&buf, bytes));
+    CU_TRY(cudaMemset(buf, 0, bytes));
+    const size_t n2 = bytes / sizeof(double2);
+    k_stream_read<<<sms * 4, 512>>>(buf, n2, d);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+      CU_TRY(cudaEventRecord(e0));
+      k_stream_read<<<sms * 4, 512>>>(buf, n2, d);
+      CU_TRY(cudaEventRecord(e1));
+      CU_TRY(cudaEventSynchronize(e1));
+      CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      best = std::max(best, (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    out_host[2] = best;
+    cudaFree(buf);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  CU_TRY(cudaGetLastError());
+  return OO_OK;
+}
+
+}  // extern "C"

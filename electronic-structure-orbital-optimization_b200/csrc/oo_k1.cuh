@@ -1,0 +1,281 @@
+// K1 — fused half-transform of the two-electron integrals (the M^4*N leading term).
+//
+// Replaces the first two pairwise contractions of the reference's 6-operand einsum
+//   torch.einsum('pqrs,pi,qj,rk,sl,ijkl', g, W, W, W, W, Gamma)
+// (electronic_structure_algorithms/orbital_optimization/base_opt_orb_solver.py:558-563) in the
+// spatial-orbital picture:  for every slab (t,q) of the ERI tensor g[t][q][r][s]
+//
+//      Y_tq[k][l] = sum_{r,s} U[r][k] * g[t][q][r][s] * U[s][l]         (N x N per slab)
+//
+// Each slab (M x M doubles, contiguous) is streamed from HBM exactly once by TMA into a multi-stage
+// shared-memory ring (128B-swizzled boxes of 256 rows x 16 columns), and contracted twice on the
+// FP64 tensor cores (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) without the intermediate ever leaving
+// registers:
+//      Z^T[l][r]  = sum_s U[s][l] * g[r][s]      A = U^T (smem), B = g tile (smem, swizzled)
+//      Y^T[l][k] += sum_r Z^T[l][r] * U[r][k]    A = Z^T accumulator fragments (register reuse:
+//                                                 the 8x8 C fragment of m8n8k4 is two 8x4 A
+//                                                 fragments with a permuted k order), B = U^T (smem)
+// Work decomposition: persistent CTAs (one per SM), slabs dealt round-robin; inside a CTA one TMA
+// producer warp and 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
+// the current 256-row pass and all of its columns, so the second contraction costs 8*NT^2/NT... a
+// fixed N/M fraction of the first.
+#pragma once
+#include "oo_common.cuh"
+
+namespace oo {
+
+constexpr int K1_NWARP = 8;                        // consumer warps per CTA
+constexpr int K1_RB = 4;                           // 8-row blocks per consumer warp per pass
+constexpr int K1_ROWS = K1_NWARP * K1_RB * 8;      // slab rows per pass = TMA box height (256)
+constexpr int K1_KC = 16;                          // slab columns per stage (128 B swizzle span)
+constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
+constexpr int K1_THREADS = (K1_NWARP + 1) * 32;    // + 1 producer warp
+
+struct K1Params {
+  const double* U;       // [M][N] row-major partial unitary
+  double* Y;             // [nslab][Np][Np], element (l,k) of slab = Y_tq[k][l]
+  const int* done_flag;  // optional: non-zero => kernel is a no-op (optimiser already stopped)
+  int M, N;
+  int nslab;             // number of (t,q) slabs owned by this GPU (= Mloc * M)
+  int nstage;            // TMA ring depth
+  int Mk;                // M rounded up to a multiple of K1_KC
+  int upitch;            // row pitch (doubles) of the transposed U copy in smem: Mk + 8
+};
+
+// Dynamic shared memory needed by k1_half_transform<NT> (before 1024 B alignment slack).
+static inline size_t k1_smem_bytes(int NT, int Mk, int nstage) {
+  const int Np = NT * 8;
+  size_t b = (size_t)nstage * K1_STAGE_BYTES;           // TMA ring
+  b += (size_t)Np * (Mk + 8) * sizeof(double);          // Ut
+  b += (size_t)K1_NWARP * Np * Np * sizeof(double);     // per-warp partial Y
+  b += (size_t)2 * nstage * sizeof(uint64_t);           // full/empty mbarriers
+  return b + 1024;                                      // alignment slack
+}
+
+template <int NT>
+struct K1Frag {
+  double g[K1_RB][2];  // B operand: g[row][s], two consecutive k4 steps
+  double u[NT][2];     // A operand: U[s][l]
+};
+
+// 2 k4-steps x RB row-blocks x NT column tiles of DMMA on one fragment set.  FULL = every
+// row-block of this warp is inside the slab (no predicates, no WARPSYNC in the hot loop).
+template <int NT, bool FULL>
+__device__ __forceinline__ void k1_mma_chunk(double (&acc)[K1_RB][NT][2], const K1Frag<NT>& f,
+                                             const bool (&act)[K1_RB]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int rb = 0; rb < K1_RB; ++rb)
+      if (FULL || act[rb]) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          dmma884(acc[rb][nt][0], acc[rb][nt][1], f.u[nt][j], f.g[rb][j]);
+      }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
+  constexpr int Np = NT * 8;
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+
+  extern __shared__ uint8_t k1_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(k1_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  double* Ut = reinterpret_cast<double*>(smem + (size_t)p.nstage * K1_STAGE_BYTES);
+  double* Ypart = Ut + (size_t)Np * p.upitch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ypart + K1_NWARP * Np * Np);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t stage_base = smem_u32(smem);
+  const uint32_t full_base = smem_u32(bars);
+  const uint32_t empty_base = full_base + 8u * p.nstage;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(full_base + 8u * s, 1);
+      mbar_init(empty_base + 8u * s, K1_NWARP);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  // Transposed, zero-padded copy of U: Ut[l][s] = U[s][l].
+  for (int idx = tid; idx < Np * p.upitch; idx += K1_THREADS) {
+    const int l = idx / p.upitch, s = idx - l * p.upitch;
+    Ut[idx] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+  }
+  __syncthreads();
+
+  const int npass = (p.M + K1_ROWS - 1) / K1_ROWS;
+  const int nkc = p.Mk / K1_KC;
+  const int nrb_total = (p.M + 7) / 8;
+  int nmine = 0;
+  if ((int)blockIdx.x < p.nslab) nmine = (p.nslab - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+  const long total_chunks = (long)nmine * npass * nkc;
+
+  if (warp == K1_NWARP) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+        for (int pass = 0; pass < npass; ++pass) {
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(empty_base + 8u * stage, phase ^ 1u);
+            mbar_arrive_expect_tx(full_base + 8u * stage, K1_STAGE_BYTES);
+            tma_load_3d(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
+                        pass * K1_ROWS, slab, full_base + 8u * stage);
+            if (++stage == p.nstage) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------- consumers ---------------------------------
+  const int g = lane >> 2, c = lane & 3;
+  // MMA column n=g of the B operand maps to slab row (8*block + rho): rows whose swizzle phases
+  // differ in bit 2 sit in the same quarter-warp, which makes every LDS.128 conflict-free.
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  // Byte offset of this lane's 16 B (two doubles: columns 2c, 2c+1 of the k8 half) inside an
+  // 8-row block of a swizzled stage; half h in {0,1} selects columns [8h, 8h+8).
+  uint32_t goff[2];
+  goff[0] = (uint32_t)(rho * 128 + (((0 * 4 + c) ^ rho) << 4));
+  goff[1] = (uint32_t)(rho * 128 + (((1 * 4 + c) ^ rho) << 4));
+  const uint32_t ut_base = smem_u32(Ut);
+  // A operand for GEMM 1: lane reads Ut[nt*8+g][col + 2c .. 2c+1]
+  const uint32_t uoff_a = (uint32_t)((g * p.upitch + 2 * c) * 8);
+  // B operand for GEMM 2: lane reads Ut[nt*8+g][row + c] and [row + c + 4]
+  const uint32_t uoff_b = (uint32_t)((g * p.upitch + c) * 8);
+  const uint32_t u_nt_stride = (uint32_t)(8 * p.upitch * 8);
+
+  double acc[K1_RB][NT][2];   // Z^T fragments of the current pass
+  double yacc[NT][NT][2];     // Y^T fragments of the current slab
+#pragma unroll
+  for (int rb = 0; rb < K1_RB; ++rb)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[rb][nt][0] = acc[rb][nt][1] = 0.0;
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b) yacc[a][b][0] = yacc[a][b][1] = 0.0;
+
+  auto load_frag = [&](K1Frag<NT>& f, int stage, int kc, int half) {
+    const uint32_t sb = stage_base + (uint32_t)stage * K1_STAGE_BYTES + goff[half];
+#pragma unroll
+    for (int rb = 0; rb < K1_RB; ++rb)
+      lds128(f.g[rb][0], f.g[rb][1], sb + (uint32_t)((rb * K1_NWARP + warp) * 1024));
+    const uint32_t ub = ut_base + uoff_a + (uint32_t)((kc * K1_KC + half * 8) * 8);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) lds128(f.u[nt][0], f.u[nt][1], ub + nt * u_nt_stride);
+  };
+
+  int stage = 0;
+  uint32_t phase = 0;
+  int slab = blockIdx.x, pass = 0, kc = 0;
+  int nrb_pass = min(K1_NWARP * K1_RB, nrb_total);  // active row-blocks in the current pass
+
+  K1Frag<NT> f0, f1;
+  if (total_chunks > 0) {
+    mbar_wait(full_base, 0);
+    load_frag(f0, 0, 0, 0);
+  }
+
+  for (long ci = 0; ci < total_chunks; ++ci) {
+    bool act[K1_RB];
+#pragma unroll
+    for (int rb = 0; rb < K1_RB; ++rb) act[rb] = (rb * K1_NWARP + warp) < nrb_pass;
+    const bool full = nrb_pass == K1_NWARP * K1_RB;
+
+    load_frag(f1, stage, kc, 1);
+    if (full) k1_mma_chunk<NT, true>(acc, f0, act);
+    else k1_mma_chunk<NT, false>(acc, f0, act);
+
+    // Prefetch the first half of the next chunk (next stage of the ring).
+    int nstage_i = stage + 1;
+    uint32_t nphase = phase;
+    if (nstage_i == p.nstage) {
+      nstage_i = 0;
+      nphase ^= 1u;
+    }
+    int nkc_i = kc + 1, npass_i = pass, nslab_i = slab;
+    if (nkc_i == nkc) {
+      nkc_i = 0;
+      if (++npass_i == npass) {
+        npass_i = 0;
+        nslab_i += gridDim.x;
+      }
+    }
+    if (ci + 1 < total_chunks) {
+      mbar_wait(full_base + 8u * nstage_i, nphase);
+      load_frag(f0, nstage_i, nkc_i, 0);
+    }
+
+    if (full) k1_mma_chunk<NT, true>(acc, f1, act);
+    else k1_mma_chunk<NT, false>(acc, f1, act);
+
+    // All shared-memory reads of `stage` are complete (their values fed the MMAs above).
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_base + 8u * stage);
+
+    if (kc == nkc - 1) {
+      // ---- end of pass: Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over this warp's rows ----
+#pragma unroll
+      for (int rb = 0; rb < K1_RB; ++rb) {
+        if (act[rb]) {
+          const int row0 = pass * K1_ROWS + (rb * K1_NWARP + warp) * 8;
+          const uint32_t ub = ut_base + uoff_b + (uint32_t)(row0 * 8);
+#pragma unroll
+          for (int nk = 0; nk < NT; ++nk) {
+            const double b0 = lds64(ub + nk * u_nt_stride);        // U[row0 + c    ][nk*8+g]
+            const double b1 = lds64(ub + nk * u_nt_stride + 32);   // U[row0 + c + 4][nk*8+g]
+#pragma unroll
+            for (int nl = 0; nl < NT; ++nl) {
+              dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][0], b0);
+              dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][1], b1);
+            }
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[rb][nt][0] = acc[rb][nt][1] = 0.0;
+      }
+      if (pass == npass - 1) {
+        // ---- end of slab: fixed-order reduction of the 8 per-warp partials, store Y^T ----
+        named_bar_sync(1, K1_NWARP * 32);  // previous slab's readers are done with Ypart
+        double* mine = Ypart + warp * Np * Np;
+#pragma unroll
+        for (int nl = 0; nl < NT; ++nl)
+#pragma unroll
+          for (int nk = 0; nk < NT; ++nk) {
+            double2 v = make_double2(yacc[nl][nk][0], yacc[nl][nk][1]);
+            *reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c) = v;
+            yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
+          }
+        named_bar_sync(1, K1_NWARP * 32);
+        double* out = p.Y + (size_t)slab * Np * Np;
+        for (int e = tid; e < Np * Np; e += K1_NWARP * 32) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < K1_NWARP; ++w) s += Ypart[w * Np * Np + e];
+          out[e] = s;
+        }
+      }
+    }
+
+    stage = nstage_i;
+    phase = nphase;
+    kc = nkc_i;
+    if (npass_i != pass || nslab_i != slab) {
+      pass = npass_i;
+      slab = nslab_i;
+      nrb_pass = min(K1_NWARP * K1_RB, nrb_total - pass * K1_NWARP * K1_RB);
+    }
+  }
+}
+
+}  // namespace oo

@@ -1,0 +1,287 @@
+// K3 — Stiefel retraction, Barzilai-Borwein step and the stopping-rule state machine, fused into a
+// single one-CTA kernel so that an optimiser iteration needs no host round trip.
+//
+// Restates (reference: electronic_structure_algorithms/orbital_optimization/
+//           partial_unitary_projection_optimizer.py)
+//   orth(V) = V Q diag(L)^(-1/2) Q^T, (L,Q) = eigh(V^T V)                     :70-83
+//   BB step:  odd k   alpha = <dU,dU> / |<dU,dG>|                              :143-148
+//             even k  alpha = |<dU,dG>| / <dG,dG>   (k != 0)                   :150-155
+//             U_{k+1} = orth(U_k - alpha G_k)                                  :157
+//   driver:   three hand-unrolled iterations then `while S[0] > tol and k <= maxiter`,
+//             S_k = (1-d)|dE| + d S_{k-1} with the one-step lag of the loop body   :176-350
+// The N x N symmetric eigenproblem (N <= 32) is solved by a cyclic two-sided Jacobi iteration in
+// shared memory (round-robin pairing, N/2 rotations in parallel).
+#pragma once
+#include "oo_common.cuh"
+
+namespace oo {
+
+constexpr int K3_THREADS = 256;
+constexpr int K3_NMAX = 32;
+
+struct OptState {
+  double alpha;      // current BB step size (reference: self._BBstepsize)
+  double P4[3];      // [f(U_k), f(U_{k-1}), f(U_{k-2})]
+  double S[2];       // [S_k, S_{k-1}]
+  double tol;        // stopping_tolerance
+  double decay;      // decay_factor
+  double E_final;    // reference return value P4_array[0]
+  int k;             // iteration_number
+  int maxiter;
+  int done;          // stop flag (kernels become no-ops when set)
+  int k_final;       // iteration_number at loop exit
+  int nan_flag;      // set when a non-finite value is met
+  int pad;
+};
+
+// Symmetric eigen-decomposition A = Q diag(w) Q^T of an n x n matrix held in shared memory.
+// On exit A holds the (almost) diagonal matrix and Q the eigenvectors as columns.
+// Parallel cyclic Jacobi, all threads of the CTA must call.  lda = K3_NMAX + 1.
+__device__ inline void jacobi_eigh_smem(double* A, double* Q, double* cs, int n, int* sflag) {
+  constexpr int LD = K3_NMAX + 1;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int ne = (n + 1) & ~1;  // players in the round-robin tournament (dummy if n is odd)
+  for (int idx = tid; idx < n * n; idx += nth) {
+    const int i = idx / n, j = idx - i * n;
+    Q[i * LD + j] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    // convergence: off-diagonal Frobenius norm relative to the diagonal
+    if (tid == 0) {
+      double off = 0.0, dia = 0.0;
+      for (int i = 0; i < n; ++i) {
+        dia += A[i * LD + i] * A[i * LD + i];
+        for (int j = i + 1; j < n; ++j) off += A[i * LD + j] * A[i * LD + j];
+      }
+      *sflag = (off <= 1e-31 * dia) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*sflag) break;
+    for (int round = 0; round < ne - 1; ++round) {
+      // pair m of this round: players (round-robin "circle" method)
+      if (tid < ne / 2) {
+        int a = (tid == 0) ? ne - 1 : (round + tid) % (ne - 1);
+        int b = (round + ne - 1 - tid) % (ne - 1);
+        int p = min(a, b), q = max(a, b);
+        double c = 1.0, s = 0.0;
+        if (q < n) {
+          const double apq = A[p * LD + q];
+          if (apq != 0.0) {
+            const double app = A[p * LD + p], aqq = A[q * LD + q];
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+        }
+        cs[4 * tid + 0] = c;
+        cs[4 * tid + 1] = s;
+        cs[4 * tid + 2] = (double)p;
+        cs[4 * tid + 3] = (double)q;
+      }
+      __syncthreads();
+      // A <- J^T A  (rows p,q)
+      for (int idx = tid; idx < (ne / 2) * n; idx += nth) {
+        const int m = idx / n, col = idx - m * n;
+        const int p = (int)cs[4 * m + 2], q = (int)cs[4 * m + 3];
+        if (q < n) {
+          const double c = cs[4 * m], s = cs[4 * m + 1];
+          const double x = A[p * LD + col], y = A[q * LD + col];
+          A[p * LD + col] = c * x - s * y;
+          A[q * LD + col] = s * x + c * y;
+        }
+      }
+      __syncthreads();
+      // A <- A J (columns p,q);  Q <- Q J
+      for (int idx = tid; idx < (ne / 2) * n; idx += nth) {
+        const int m = idx / n, row = idx - m * n;
+        const int p = (int)cs[4 * m + 2], q = (int)cs[4 * m + 3];
+        if (q < n) {
+          const double c = cs[4 * m], s = cs[4 * m + 1];
+          const double x = A[row * LD + p], y = A[row * LD + q];
+          A[row * LD + p] = c * x - s * y;
+          A[row * LD + q] = s * x + c * y;
+          const double u = Q[row * LD + p], v = Q[row * LD + q];
+          Q[row * LD + p] = c * u - s * v;
+          Q[row * LD + q] = s * u + c * v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// U_out = orth(V) for an M x N matrix V in global memory.  One CTA.  V and U_out may alias.
+// smem: sA, sQ, sS are (K3_NMAX)*(K3_NMAX+1) doubles each; cs 4*K3_NMAX doubles.
+__device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
+                                   double* sQ, double* sS, double* cs, int* sflag) {
+  constexpr int LD = K3_NMAX + 1;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  // Gram matrix V^T V (upper triangle computed, mirrored)
+  for (int idx = tid; idx < N * N; idx += nth) {
+    const int i = idx / N, j = idx - i * N;
+    if (j >= i) {
+      double s = 0.0;
+      for (int t = 0; t < M; ++t) s = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s);
+      sA[i * LD + j] = s;
+      sA[j * LD + i] = s;
+    }
+  }
+  __syncthreads();
+  jacobi_eigh_smem(sA, sQ, cs, N, sflag);
+  __syncthreads();
+  // S = Q diag(w^-1/2) Q^T
+  for (int idx = tid; idx < N * N; idx += nth) {
+    const int i = idx / N, j = idx - i * N;
+    double s = 0.0;
+    for (int m = 0; m < N; ++m) s += sQ[i * LD + m] * sQ[j * LD + m] / sqrt(sA[m * LD + m]);
+    sS[i * LD + j] = s;
+  }
+  __syncthreads();
+  // U = V S ; row-wise so V and Uout may alias (each thread owns whole rows)
+  for (int t = tid; t < M; t += nth) {
+    double v[K3_NMAX];
+    for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j];
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int m = 0; m < N; ++m) s = fma(v[m], sS[m * LD + j], s);
+      Uout[(size_t)t * N + j] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uout, int M, int N) {
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
+      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX];
+  __shared__ int sflag;
+  retract_cta(V, Uout, M, N, sA, sQ, sS, cs, &sflag);
+}
+
+struct StepParams {
+  OptState* st;
+  double* Ucur;         // U_k        -> becomes U_{k+1}
+  double* Uprev;        // U_{k-1}    -> becomes U_k
+  const double* gE;     // [M*N+1] gradient at U_k and f(U_k) (already all-reduced)
+  double* Gprev;        // G_{k-1}    -> becomes G_k
+  double* Vtmp;         // scratch M*N
+  double* E_hist;       // E_hist[k] = f(U_k)
+  int M, N;
+  int hist_cap;
+};
+
+// One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
+__global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
+      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+  __shared__ int sflag;
+  OptState* st = p.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int MN = p.M * p.N;
+  const int k = st->k;
+  const double fk = p.gE[MN];
+  double alpha = st->alpha;
+  double P0 = st->P4[0], P1 = st->P4[1], P2 = st->P4[2], S0 = st->S[0], S1 = st->S[1];
+  const double d = st->decay;
+  bool stop = false;
+
+  if (k == 0) {
+    P2 = fk;                                   // P4_array[2] = f(U_0)
+  } else if (k == 1) {
+    P1 = fk;                                   // P4_array[1] = f(U_1)
+    S0 = (1.0 - d) * fabs(P1 - P2) + d * S1;   // S_1, with S1 preset to 1.5*tol
+  } else if (k == 2) {
+    P0 = fk;                                   // P4_array[0] = f(U_2)
+    S1 = S0;                                   // np.roll(St_array, 1) on a 2-vector = swap
+    S0 = (1.0 - d) * fabs(P0 - P1) + d * S1;   // S_2
+  } else {
+    // `while St_array[0] > tol and iteration_number <= maxiter`
+    if (!(S0 > st->tol && k <= st->maxiter)) {
+      stop = true;
+    } else {
+      P2 = P1; P1 = P0; P0 = fk;               // roll, then P4_array[0] = f(U_k)
+      const double s_old = S0;
+      S1 = s_old;
+      S0 = (1.0 - d) * fabs(P1 - P2) + d * S1; // lagged difference, as in the reference loop body
+    }
+  }
+  __syncthreads();  // every thread has read the state before thread 0 rewrites it
+
+  if (stop) {
+    if (tid == 0) {
+      st->done = 1;
+      st->k_final = k;
+      st->E_final = P0;                        // reference returns P4_array[0] = f(U_{k-1})
+    }
+    return;
+  }
+  if (tid == 0 && k < p.hist_cap) p.E_hist[k] = fk;
+
+  // ---- BB step size -------------------------------------------------------
+  if (k >= 1) {
+    double uu = 0.0, ug = 0.0, gg = 0.0;
+    for (int i = tid; i < MN; i += nth) {
+      const double du = p.Ucur[i] - p.Uprev[i];
+      const double dg = p.gE[i] - p.Gprev[i];
+      uu = fma(du, du, uu);
+      ug = fma(du, dg, ug);
+      gg = fma(dg, dg, gg);
+    }
+    uu = block_sum(uu, scratch);
+    ug = block_sum(ug, scratch);
+    gg = block_sum(gg, scratch);
+    alpha = (k & 1) ? uu / fabs(ug) : fabs(ug) / gg;
+  }
+  // ---- V = U_k - alpha G_k; shift histories ---------------------------------
+  for (int i = tid; i < MN; i += nth) {
+    const double u = p.Ucur[i], g = p.gE[i];
+    p.Vtmp[i] = u - alpha * g;
+    p.Uprev[i] = u;
+    p.Gprev[i] = g;
+  }
+  __syncthreads();
+  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sQ, sS, cs, &sflag);
+  if (tid == 0) {
+    st->alpha = alpha;
+    st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
+    st->S[0] = S0; st->S[1] = S1;
+    st->k = k + 1;
+    if (!isfinite(alpha) || !isfinite(fk)) st->nan_flag = 1;
+  }
+}
+
+// Standalone BB update (compute_updated_partial_unitary, pupo.py:129-159) for API parity.
+struct BBParams {
+  const double* Ucur; const double* Uprev; const double* Gcur; const double* Gprev;
+  double* Unew; double* Vtmp; double* alpha_io; int iteration; int M, N;
+};
+__global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
+      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+  __shared__ int sflag;
+  const int tid = threadIdx.x, nth = blockDim.x, MN = p.M * p.N;
+  double alpha = *p.alpha_io;
+  __syncthreads();
+  if (p.iteration >= 1) {
+    double uu = 0.0, ug = 0.0, gg = 0.0;
+    for (int i = tid; i < MN; i += nth) {
+      const double du = p.Ucur[i] - p.Uprev[i];
+      const double dg = p.Gcur[i] - p.Gprev[i];
+      uu = fma(du, du, uu);
+      ug = fma(du, dg, ug);
+      gg = fma(dg, dg, gg);
+    }
+    uu = block_sum(uu, scratch);
+    ug = block_sum(ug, scratch);
+    gg = block_sum(gg, scratch);
+    alpha = (p.iteration & 1) ? uu / fabs(ug) : fabs(ug) / gg;
+  }
+  for (int i = tid; i < MN; i += nth) p.Vtmp[i] = p.Ucur[i] - alpha * p.Gcur[i];
+  __syncthreads();
+  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sQ, sS, cs, &sflag);
+  if (tid == 0) *p.alpha_io = alpha;
+}
+
+}  // namespace oo

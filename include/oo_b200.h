@@ -1,0 +1,138 @@
+/*
+ * oo_b200.h — C ABI of liboo_b200.so: the B200 (sm_100a) implementation of the orbital-optimisation
+ * inner loop of OptOrbVQE (energy E(U) and gradient dE/dU of the partial-unitary projection
+ * optimiser, Stiefel retraction, Barzilai-Borwein step).
+ *
+ * The reference (JoelHBierman/electronic-structure-orbital-optimization) is pure Python and has no
+ * FFI; each entry point below names the reference code it replaces, paths relative to
+ * electronic_structure_algorithms/orbital_optimization/ :
+ *   pupo.py = partial_unitary_projection_optimizer.py,  base.py = base_opt_orb_solver.py,
+ *   eig.py  = opt_orb_eigensolver.py.
+ *
+ * Conventions
+ *   - All matrices are FP64, row-major.  "dev" pointers are CUDA device pointers on the context's
+ *     device, "host" pointers are ordinary host memory.  No torch types cross this boundary.
+ *   - Spatial-orbital picture: M orbitals in the large basis, N in the active space (N <= 32).
+ *       h  [M][M]           one-body integrals (one spin block of the reference's tensor)
+ *       g  [Mloc][M][M][M]  two-body integrals, "physicist" index order of base.py:90, rows
+ *                           t0 .. t0+Mloc-1 of the first index (the GPU's shard; Mloc = M when
+ *                           unsharded)
+ *       D  [N][N]           spin-summed, state-weighted 1-RDM
+ *       G  [N][N][N][N]     spin-summed, state-weighted 2-RDM
+ *       U  [M][N]           partial unitary
+ *     E(U) = sum h_pq U_pi U_qj D_ij + sum g_pqrs U_pi U_qj U_rk U_sl G_ijkl   (base.py:554-563)
+ *   - Every function returns 0 on success, a negative oo_status otherwise; oo_last_error() gives a
+ *     thread-local description.  Nothing aborts the process.  There is no CPU fallback: a missing
+ *     or non-sm_100 device is an error.
+ */
+#ifndef OO_B200_H
+#define OO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oo_ctx oo_ctx;
+
+enum oo_status {
+  OO_OK = 0,
+  OO_ERR_INVALID = -1,   /* bad argument / shape                                  */
+  OO_ERR_CUDA = -2,      /* CUDA runtime or driver error                          */
+  OO_ERR_STATE = -3,     /* call sequence error (integrals or RDMs not set ...)   */
+  OO_ERR_NCCL = -4,      /* NCCL not loadable or a collective failed              */
+  OO_ERR_UNSUPPORTED = -5,
+  OO_ERR_NUMERIC = -6    /* non-finite value met during the optimisation          */
+};
+
+/* oo_set_integrals flags */
+#define OO_G_V4_SYMMETRIC 1u /* caller asserts g[pqrs]=g[qpsr]=g[rspq]=g[srqp] (holds for real
+                                orbitals); enables the one-pass analytic gradient              */
+
+/* ---- library / device ---------------------------------------------------------------------- */
+const char* oo_last_error(void);
+const char* oo_version(void);
+/* Number of visible CUDA devices with compute capability 10.x; <0 on error. */
+int oo_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context per GPU (one process per GPU).  The context owns all workspaces; input tensors
+ * stay owned by the caller and must outlive their use.  Shard = rows [t0, t0+mloc) of g's first
+ * index; pass t0=0, mloc=M for a single GPU.
+ * Replaces: the implicit torch device state behind PartialUnitaryProjectionOptimizer(device=...)
+ * (pupo.py:15-48). */
+int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out);
+int oo_destroy(oo_ctx* ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all work; NULL = own stream. */
+int oo_set_stream(oo_ctx* ctx, void* cuda_stream);
+int oo_synchronize(oo_ctx* ctx);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+/* Registers (does not copy) h_dev [M][M] and g_dev [mloc][M][M][M].  M must be even (TMA global
+ * strides are multiples of 16 bytes).  Replaces the .to(device) shuttling of the integral tensors,
+ * opt_orb_minimum_eigensolver.py:219-222. */
+int oo_set_integrals(oo_ctx* ctx, const double* h_dev, const double* g_dev, unsigned flags);
+/* Max |g - g∘pi| over the three V4 permutations and max |g| of a FULL (unsharded) device tensor
+ * g_dev[M][M][M][M]; out_host[0]=max asymmetry, out_host[1]=max |g|. */
+int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_host);
+/* Spatial RDMs D_dev [N][N], G_dev [N][N][N][N]; symmetrised/padded copies are made.
+ * Replaces the per-state RDM arguments of base.py:534-538 / the state loop of eig.py:149-169
+ * (weights are folded in by the caller: E is linear in the RDMs). */
+int oo_set_rdms(oo_ctx* ctx, const double* D_dev, const double* G_dev);
+
+/* ---- evaluation ---------------------------------------------------------------------------- */
+/* Enqueue one evaluation at U_dev [M][N].  out_dev [M*N+1] receives this shard's rows of dE/dU
+ * (other rows are left untouched: zero if the buffer was zeroed once) followed by the shard's
+ * partial energy.  With one GPU that is E(U) and dE/dU.  Asynchronous on the context stream.
+ * Replaces base.py:534-582 (compute_rotated_energy) + pupo.py:85-103 (autograd gradient). */
+int oo_energy_grad(oo_ctx* ctx, const double* U_dev, double* out_dev);
+/* Same through host buffers: H2D of U, evaluation, all-reduce when a communicator is attached,
+ * D2H of E and dE/dU, synchronous.  This is the reference-facing call used for end-to-end timing. */
+int oo_energy_grad_host(oo_ctx* ctx, const double* U_host, double* E_host, double* grad_host);
+/* Rotated integrals h' [N][N], g' [N][N][N][N] (this shard's partial sum over the first index).
+ * Replaces the tensor part of get_rotated_hamiltonian, base.py:597-604, and
+ * opt_orb_mcvqe.py:90-98. */
+int oo_transform(oo_ctx* ctx, const double* U_dev, double* h_rot_dev, double* g_rot_dev);
+
+/* ---- retraction / BB step ------------------------------------------------------------------ */
+/* U_out = V (V^T V)^(-1/2).  Replaces orth(), pupo.py:70-83 and base.py:614-626. */
+int oo_orth(oo_ctx* ctx, const double* V_dev, double* U_out_dev);
+/* compute_updated_partial_unitary, pupo.py:129-159.  alpha_io_dev: BB step size in/out. */
+int oo_bb_update(oo_ctx* ctx, int iteration, const double* U_cur_dev, const double* U_prev_dev,
+                 const double* G_cur_dev, const double* G_prev_dev, double* alpha_io_dev,
+                 double* U_new_dev);
+
+/* ---- the whole inner loop ------------------------------------------------------------------ */
+/* compute_optimal_rotation, pupo.py:161-350, entirely on the device: U_io_host [M][N] is the
+ * initial partial unitary on entry and the final one on exit; *E_final = the reference's return
+ * value P4_array[0]; E_hist_host[k] = f(U_k) for k < hist_cap (callback replay);
+ * *n_iter = final iteration_number. */
+int oo_optimize(oo_ctx* ctx, double* U_io_host, double bb0, double tol, int maxiter, double decay,
+                double* E_hist_host, int hist_cap, int* n_iter, double* E_final,
+                double* bb_final);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------------------------- */
+/* 128-byte NCCL unique id, to be created on rank 0 and broadcast by the host framework. */
+int oo_nccl_unique_id(void* id128_host);
+int oo_comm_init(oo_ctx* ctx, const void* id128_host, int rank, int world);
+/* In-place sum all-reduce of count doubles on the context stream (used for the M*N+1 buffer). */
+int oo_allreduce(oo_ctx* ctx, double* buf_dev, size_t count);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+/* Average device time (ms) of the kernels of the last oo_energy_grad call, measured with CUDA
+ * events on the context stream: [0] K1 half-transform, [1] q-contraction, [2] gamma contraction,
+ * [3] one-body + finalize, [4] whole evaluation.  Requires oo_set_timing(ctx,1) beforehand. */
+int oo_set_timing(oo_ctx* ctx, int enable);
+int oo_last_timing(oo_ctx* ctx, float* ms5_host);
+/* Number of kernels launched by this context since creation. */
+long long oo_launch_count(oo_ctx* ctx);
+/* Measured FP64 peaks of the device: out_host[0] = DMMA.8x8x4 TFLOP/s (register-resident loop),
+ * out_host[1] = DFMA TFLOP/s, out_host[2] = streaming read GB/s (LDG.128 sum over `bytes`). */
+int oo_measure_peaks(int device, size_t bytes, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OO_B200_H */
