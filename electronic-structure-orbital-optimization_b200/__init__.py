@@ -1,0 +1,12 @@
+"""B200-native orbital-optimisation inner loop (energy, analytic gradient, Stiefel retraction,
+Barzilai-Borwein step) behind the reference's PartialUnitaryProjectionOptimizer API.
+
+The numerical work is done by hand-written sm_100a CUDA kernels in liboo_b200.so (C ABI:
+include/oo_b200.h); this package is the host-side mirror of the reference interface."""
+from . import _lib, ingest, synthetic
+from .engine import OrbitalEngine, measure_peaks
+from .optimizer import PartialUnitaryProjectionOptimizer, clear_engine_cache
+from .distributed import shard_range, attach_nccl
+
+__all__ = ["PartialUnitaryProjectionOptimizer", "OrbitalEngine", "measure_peaks", "shard_range",
+           "attach_nccl", "clear_engine_cache", "ingest", "synthetic"]

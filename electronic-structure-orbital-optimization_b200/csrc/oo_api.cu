@@ -377,7 +377,9 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   if (e == cudaSuccess) e = cudaMemset(c->state, 0, sizeof(OptState));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin, (MN + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin_state, 2 * sizeof(OptState));
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  // A blocking stream: it orders itself against the legacy default stream, which is where a host
+  // framework (torch) produces the input tensors unless told otherwise.
+  if (e == cudaSuccess) e = cudaStreamCreate(&c->stream);
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
     e = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming);
@@ -424,7 +426,7 @@ int oo_set_stream(oo_ctx* c, void* cuda_stream) {
   if (cuda_stream) {
     c->stream = (cudaStream_t)cuda_stream;
   } else {
-    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreate(&c->stream));
     c->own_stream = true;
   }
   return OO_OK;

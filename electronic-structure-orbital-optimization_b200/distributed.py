@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: one process per GPU, the ERI tensor sharded by its first index.
+
+Every rank holds rows [t0, t0+mloc) of g, computes its rows of dE/dU and a partial energy, and the
+only communication is one sum all-reduce of M*N+1 doubles per evaluation, issued by liboo_b200 on
+its own NCCL communicator (bootstrapped here through torch.distributed)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+
+def shard_range(M: int, rank: int, world: int) -> Tuple[int, int]:
+    """(t0, mloc): contiguous ceil-div slabs of the first index; trailing ranks may get fewer rows.
+    Every rank must own at least one row."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    if world > M:
+        raise ValueError(f"cannot shard M={M} rows over {world} ranks")
+    base, extra = divmod(M, world)
+    t0 = rank * base + min(rank, extra)
+    return t0, base + (1 if rank < extra else 0)
+
+
+def attach_nccl(engine, group=None) -> None:
+    """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed
+    (any backend) broadcasts its 128 bytes, every rank joins."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return
+    backend = dist.get_backend(group)
+    dev = engine.device if backend == "nccl" else torch.device("cpu")
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = type(engine).nccl_unique_id()
+        buf.copy_(torch.tensor(list(uid), dtype=torch.uint8))
+    dist.broadcast(buf, src=0, group=group)
+    engine.attach_comm(bytes(buf.cpu().tolist()), rank, world)

@@ -1,0 +1,254 @@
+"""OrbitalEngine — thin Python owner of one liboo_b200 context (one GPU, one shard of g).
+
+PyTorch is used only for device memory and streams; every numerical step runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dev_f64(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    if t.dtype != torch.float64:
+        raise TypeError(f"float64 tensor required, got {t.dtype}")
+    return t.to(device).contiguous()
+
+
+class OrbitalEngine:
+    """Energy / gradient / retraction engine for spatial integrals (h [M,M], g [mloc,M,M,M]).
+
+    `t0, mloc` select the shard of g's first index held by this GPU (default: everything)."""
+
+    def __init__(self, M: int, N: int, device="cuda:0", t0: int = 0, mloc: Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("OrbitalEngine runs on CUDA devices only (there is no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device is available; the B200 path has no CPU fallback")
+        self.M_user, self.N = int(M), int(N)
+        self.M = self.M_user + (self.M_user % 2)      # TMA needs 16-byte row strides: pad odd M
+        self.t0 = int(t0)
+        self.mloc_user = self.M_user - self.t0 if mloc is None else int(mloc)
+        self.mloc = self.mloc_user
+        if self.M != self.M_user and self.t0 + self.mloc_user == self.M_user:
+            self.mloc += 1                             # the padded (zero) orbital joins the last shard
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.oo_create(idx, self.M, self.N, self.t0, self.mloc, C.byref(self._ctx)))
+        self._keep = {}
+        self._out = torch.zeros(self.M * self.N + 1, dtype=torch.float64, device=self.device)
+        self.world = 1
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.oo_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs -------------------------------------------------------------------------------
+    def _inputs_ready(self) -> None:
+        """Tensors handed to the library may still be in flight on torch's current stream."""
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def _pad_h(self, h):
+        if self.M == self.M_user:
+            return h
+        out = torch.zeros(self.M, self.M, dtype=torch.float64, device=h.device)
+        out[:self.M_user, :self.M_user] = h
+        return out
+
+    def _pad_g(self, g):
+        if self.M == self.M_user:
+            return g
+        out = torch.zeros(self.mloc, self.M, self.M, self.M, dtype=torch.float64, device=g.device)
+        out[:self.mloc_user, :self.M_user, :self.M_user, :self.M_user] = g
+        return out
+
+    def _pad_u(self, U):
+        if self.M == self.M_user:
+            return U
+        out = torch.zeros(self.M, self.N, dtype=torch.float64, device=U.device)
+        out[:self.M_user] = U
+        return out
+
+    def check_v4_symmetry(self, g_full: torch.Tensor) -> Tuple[float, float]:
+        """(max |g - g∘pi| over the three V4 permutations, max |g|) of a full device tensor."""
+        g_full = _dev_f64(g_full, self.device)
+        out = (C.c_double * 2)()
+        self._inputs_ready()
+        _lib.check(self.lib.oo_check_v4_symmetry(self.device.index, _ptr(g_full), g_full.shape[0],
+                                                 out))
+        return float(out[0]), float(out[1])
+
+    def set_integrals(self, h: torch.Tensor, g: torch.Tensor, assume_v4_symmetric: bool = False,
+                      sym_rtol: float = 1e-11) -> None:
+        """h [M,M]; g [mloc,M,M,M] (this shard's rows).  The tensors are used in place (no copy)
+        when already on the device, contiguous and M is even."""
+        if tuple(h.shape) != (self.M_user, self.M_user):
+            raise ValueError(f"h must be [{self.M_user},{self.M_user}], got {tuple(h.shape)}")
+        if tuple(g.shape) != (self.mloc_user,) + (self.M_user,) * 3:
+            raise ValueError(f"g must be [{self.mloc_user},{self.M_user},{self.M_user},"
+                             f"{self.M_user}], got {tuple(g.shape)}")
+        h = self._pad_h(_dev_f64(h, self.device))
+        g = self._pad_g(_dev_f64(g, self.device))
+        if not assume_v4_symmetric:
+            if self.mloc != self.M:
+                raise ValueError("a sharded g cannot be verified locally; verify the full tensor "
+                                 "before sharding and pass assume_v4_symmetric=True")
+            asym, gmax = self.check_v4_symmetry(g)
+            if asym > sym_rtol * max(gmax, 1e-300):
+                raise NotImplementedError(
+                    f"two-body integrals are not V4-symmetric (max asymmetry {asym:.3e}, "
+                    f"max |g| {gmax:.3e}); the one-pass gradient needs g[pqrs]=g[qpsr]=g[rspq]")
+        self._keep["h"], self._keep["g"] = h, g
+        self._inputs_ready()
+        _lib.check(self.lib.oo_set_integrals(self._ctx, _ptr(h), _ptr(g), _lib.OO_G_V4_SYMMETRIC))
+
+    def set_rdms(self, D: torch.Tensor, G: torch.Tensor) -> None:
+        """Spatial spin-summed (and state-weighted) D [N,N], Gamma [N,N,N,N]."""
+        N = self.N
+        if tuple(D.shape) != (N, N) or tuple(G.shape) != (N, N, N, N):
+            raise ValueError(f"RDM shapes {tuple(D.shape)} {tuple(G.shape)} do not match N={N}")
+        D, G = _dev_f64(D, self.device), _dev_f64(G, self.device)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_set_rdms(self._ctx, _ptr(D), _ptr(G)))
+        _lib.check(self.lib.oo_synchronize(self._ctx))   # D, G may be freed by the caller now
+
+    # -- multi-GPU -----------------------------------------------------------------------------
+    def attach_comm(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.oo_comm_init(self._ctx, buf, rank, world))
+        self.world = world
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        _lib.check(_lib.load().oo_nccl_unique_id(buf))
+        return bytes(buf)
+
+    # -- evaluation ----------------------------------------------------------------------------
+    def energy_grad(self, U: torch.Tensor, allreduce: bool = True):
+        """(E 0-dim tensor, dE/dU [M,N]) on the device, asynchronous w.r.t. the host."""
+        U = self._pad_u(_dev_f64(U, self.device))
+        self._inputs_ready()
+        _lib.check(self.lib.oo_energy_grad(self._ctx, _ptr(U), _ptr(self._out)))
+        if allreduce and self.world > 1:
+            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(self._out), self.M * self.N + 1))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+        MN = self.M * self.N
+        grad = self._out[:MN].view(self.M, self.N)[:self.M_user].clone()
+        return self._out[MN].clone(), grad
+
+    def energy_grad_host(self, U: np.ndarray):
+        """Host-buffer entry point: (E float, dE/dU ndarray); H2D/D2H inside the call."""
+        Uh = np.zeros((self.M, self.N), dtype=np.float64)
+        Uh[:self.M_user] = np.asarray(U, dtype=np.float64)
+        E = C.c_double()
+        grad = np.empty((self.M, self.N), dtype=np.float64)
+        _lib.check(self.lib.oo_energy_grad_host(self._ctx, Uh.ctypes.data_as(C.c_void_p),
+                                                C.byref(E), grad.ctypes.data_as(C.c_void_p)))
+        return float(E.value), grad[:self.M_user]
+
+    def transform(self, U: torch.Tensor):
+        """Rotated integrals (h' [N,N], g' [N,N,N,N]) on the device (shard-partial when sharded)."""
+        U = self._pad_u(_dev_f64(U, self.device))
+        N = self.N
+        h_rot = torch.zeros(N, N, dtype=torch.float64, device=self.device)
+        g_rot = torch.zeros(N, N, N, N, dtype=torch.float64, device=self.device)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_transform(self._ctx, _ptr(U), _ptr(h_rot), _ptr(g_rot)))
+        if self.world > 1:
+            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(h_rot), N * N))
+            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(g_rot), N ** 4))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+        return h_rot, g_rot
+
+    def orth(self, V: torch.Tensor) -> torch.Tensor:
+        V = self._pad_u(_dev_f64(V, self.device))
+        out = torch.empty_like(V)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_orth(self._ctx, _ptr(V), _ptr(out)))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+        return out[:self.M_user]
+
+    def bb_update(self, iteration, U_cur, U_prev, G_cur, G_prev, stepsize: float):
+        """compute_updated_partial_unitary: returns (U_next [M,N] device tensor, new step size)."""
+        U_cur = self._pad_u(_dev_f64(U_cur, self.device))
+        G_cur = self._pad_u(_dev_f64(G_cur, self.device))
+        U_prev = None if U_prev is None else self._pad_u(_dev_f64(U_prev, self.device))
+        G_prev = None if G_prev is None else self._pad_u(_dev_f64(G_prev, self.device))
+        alpha = torch.tensor([float(stepsize)], dtype=torch.float64, device=self.device)
+        out = torch.empty_like(U_cur)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_bb_update(self._ctx, int(iteration), _ptr(U_cur), _ptr(U_prev),
+                                         _ptr(G_cur), _ptr(G_prev), _ptr(alpha), _ptr(out)))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+        return out[:self.M_user], float(alpha.item())
+
+    def optimize(self, U0, bb0: float, tol: float, maxiter: int, decay: float = 0.8):
+        """The whole inner loop on the device.  Returns dict(U ndarray, energy, n_iter, E_hist,
+        stepsize)."""
+        Uh = np.zeros((self.M, self.N), dtype=np.float64)
+        Uh[:self.M_user] = np.asarray(U0, dtype=np.float64)
+        cap = max(int(maxiter), 0) + 8
+        hist = np.zeros(cap, dtype=np.float64)
+        n_iter, E, bb = C.c_int(), C.c_double(), C.c_double()
+        _lib.check(self.lib.oo_optimize(self._ctx, Uh.ctypes.data_as(C.c_void_p), float(bb0),
+                                        float(tol), int(maxiter), float(decay),
+                                        hist.ctypes.data_as(C.c_void_p), cap, C.byref(n_iter),
+                                        C.byref(E), C.byref(bb)))
+        return {"U": Uh[:self.M_user].copy(), "energy": float(E.value), "n_iter": int(n_iter.value),
+                "E_hist": hist, "stepsize": float(bb.value)}
+
+    # -- measurement ---------------------------------------------------------------------------
+    def use_stream(self, stream: Optional["torch.cuda.Stream"]) -> None:
+        """Run all library work on a torch stream (so torch.cuda.Event timing sees it); None
+        returns to a library-owned stream."""
+        self._keep["stream"] = stream
+        handle = C.c_void_p(0 if stream is None else stream.cuda_stream)
+        _lib.check(self.lib.oo_set_stream(self._ctx, handle))
+
+    def set_timing(self, on: bool) -> None:
+        _lib.check(self.lib.oo_set_timing(self._ctx, 1 if on else 0))
+
+    def last_timing(self):
+        ms = (C.c_float * 5)()
+        _lib.check(self.lib.oo_last_timing(self._ctx, ms))
+        return [float(x) for x in ms]
+
+    def launch_count(self) -> int:
+        return int(self.lib.oo_launch_count(self._ctx))
+
+    def enqueue_energy_grad(self, U_dev: torch.Tensor, allreduce: bool = True) -> None:
+        """Asynchronous evaluation into the engine's output buffer (bench inner loop)."""
+        _lib.check(self.lib.oo_energy_grad(self._ctx, _ptr(U_dev), _ptr(self._out)))
+        if allreduce and self.world > 1:
+            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(self._out), self.M * self.N + 1))
+
+    def synchronize(self) -> None:
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+
+
+def measure_peaks(device_index: int = 0, nbytes: int = 8 << 30):
+    """(DMMA TFLOP/s, DFMA TFLOP/s, streaming-read GB/s) measured on the device."""
+    out = (C.c_double * 3)()
+    _lib.check(_lib.load().oo_measure_peaks(device_index, nbytes, out))
+    return float(out[0]), float(out[1]), float(out[2])

@@ -1,0 +1,293 @@
+"""Drop-in PartialUnitaryProjectionOptimizer backed by the B200 CUDA library.
+
+Mirrors the constructor, properties, method names, argument meaning and return types of the
+reference class (electronic_structure_algorithms/orbital_optimization/
+partial_unitary_projection_optimizer.py:7-350) so that the unmodified outer loops
+(opt_orb_minimum_eigensolver.py:219-228, opt_orb_eigensolver.py:243-252) can use it:
+
+    optimizer.compute_optimal_rotation(fun=solver.compute_rotated_energy, oneRDM=..., twoRDM=...,
+        one_body_integrals=..., two_body_integrals=..., initial_partial_unitary=...)[0]
+
+Differences, all deliberate:
+  * the energy, its gradient (analytic, no autograd graph), the retraction, the BB step and the
+    stopping rule run inside liboo_b200 on the GPU; there is no CPU path (device must be 'cuda*');
+  * `fun` is only *identified* (compute_rotated_energy / compute_rotated_weighted_energy_sum), not
+    called; an arbitrary callable raises TypeError;
+  * user callbacks are replayed, in order and with the reference's arguments, after the device
+    loop has finished (same (iteration, energy) pairs, different wall-clock moment);
+  * instances hold no device handles, so `copy.deepcopy` (base_opt_orb_solver.py:75) is safe;
+    engines are cached in a module-level registry keyed by the integral tensors.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ingest
+from .engine import OrbitalEngine
+
+_RECOGNISED = ("compute_rotated_energy", "compute_rotated_weighted_energy_sum")
+
+# (device index, data_ptr, _version, shape) of the two-body tensor -> (engine, structure)
+_ENGINE_CACHE = {}
+_ENGINE_CACHE_MAX = 2
+
+
+def _fun_identity(fun) -> Tuple[str, object]:
+    """(name, bound instance or None) of the objective passed by the outer loop."""
+    target = fun
+    while hasattr(target, "func") and not hasattr(target, "__func__"):   # functools.partial
+        target = target.func
+    name = getattr(getattr(target, "__func__", target), "__name__", None)
+    if name not in _RECOGNISED:
+        raise TypeError(
+            "fun must be BaseOptOrbSolver.compute_rotated_energy or "
+            "OptOrbEigensolver.compute_rotated_weighted_energy_sum (got %r); the CUDA path "
+            "evaluates that functional itself and cannot call arbitrary objectives" % (fun,))
+    return name, getattr(target, "__self__", None)
+
+
+def clear_engine_cache() -> None:
+    for eng, _ in _ENGINE_CACHE.values():
+        eng.close()
+    _ENGINE_CACHE.clear()
+
+
+class PartialUnitaryProjectionOptimizer:
+    """Gradient-projection optimiser over M x N real partial unitaries with alternating
+    Barzilai-Borwein step (reference: partial_unitary_projection_optimizer.py:7)."""
+
+    def __init__(self,
+                 initial_BBstepsize: float,
+                 stopping_tolerance: float,
+                 maxiter: int,
+                 callback: Optional[Callable] = None,
+                 decay_factor: float = 0.8,
+                 gradient_method: Optional[str] = 'autograd',
+                 device: Optional[str] = 'cuda') -> None:
+        if gradient_method not in ('autograd', 'finite_difference'):
+            raise ValueError("gradient_method must be 'autograd' or 'finite_difference'")
+        if not str(device).startswith('cuda'):
+            raise ValueError("this implementation runs on CUDA devices only (device='cuda[:n]'); "
+                             "use the reference class for device='cpu'")
+        self._callback = callback
+        self.stopping_tolerance = stopping_tolerance
+        self.maxiter = maxiter
+        self._BBstepsize = initial_BBstepsize
+        self.decay_factor = decay_factor
+        self.device = device
+        self.gradient_method = gradient_method
+        self.last_result = None      # bookkeeping of the most recent compute_optimal_rotation
+
+    # -- properties of the reference (pupo.py:50-68) -------------------------------------------
+    @property
+    def callback(self) -> Callable:
+        return self._callback
+
+    @callback.setter
+    def callback(self, func: Callable) -> None:
+        self._callback = func
+
+    @property
+    def BBstepsize(self) -> float:
+        return self._BBstepsize
+
+    @BBstepsize.setter
+    def BBstepsize(self, stepsize: float) -> None:
+        self._BBstepsize = stepsize
+
+    # -- engine plumbing -----------------------------------------------------------------------
+    def _torch_device(self) -> torch.device:
+        d = torch.device(self.device)
+        return torch.device('cuda', d.index if d.index is not None else torch.cuda.current_device())
+
+    def _engine_for(self, one_body_integrals: torch.Tensor, two_body_integrals: torch.Tensor):
+        dev = self._torch_device()
+        # The outer loops re-create the device tensors every iteration (.to(device) / .to('cpu'),
+        # opt_orb_minimum_eigensolver.py:219-235), so identity is useless as a key: use a content
+        # fingerprint (one streaming pass, negligible next to the H2D copy the caller just paid).
+        h_dev, g_dev = one_body_integrals.to(dev), two_body_integrals.to(dev)
+        flat = g_dev.reshape(-1)
+        key = (dev.index, tuple(g_dev.shape), self._n_active, float(flat.sum()),
+               float(flat[::7].sum()), float(flat.abs().max()), float(h_dev.sum()))
+        hit = _ENGINE_CACHE.get(key)
+        if hit is not None:
+            return hit
+        h_sp, g_sp, structure = ingest.reduce_integrals(h_dev, g_dev)
+        while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
+            old_key = next(iter(_ENGINE_CACHE))
+            _ENGINE_CACHE.pop(old_key)[0].close()
+        eng = OrbitalEngine(structure.M, self._n_active, device=dev)
+        eng.set_integrals(h_sp, g_sp)
+        _ENGINE_CACHE[key] = (eng, structure)
+        return eng, structure
+
+    def _prepare(self, fun, oneRDM, twoRDM, one_body_integrals, two_body_integrals, n_active: int):
+        name, owner = _fun_identity(fun)
+        weights = None
+        if name == "compute_rotated_weighted_energy_sum":
+            weights = list(getattr(owner, "weight_vector"))
+            if not isinstance(oneRDM, (list, tuple)):
+                raise TypeError("compute_rotated_weighted_energy_sum needs lists of RDMs")
+        elif isinstance(oneRDM, (list, tuple)):
+            raise TypeError("compute_rotated_energy takes single RDM tensors, not lists")
+        self._n_active = n_active
+        eng, structure = self._engine_for(one_body_integrals, two_body_integrals)
+        if eng.N != n_active:
+            raise ValueError("active-space size changed for cached integrals")
+        dev = self._torch_device()
+        ones = [d.to(dev) for d in oneRDM] if weights is not None else oneRDM.to(dev)
+        twos = [g.to(dev) for g in twoRDM] if weights is not None else twoRDM.to(dev)
+        D_sp, G_sp = ingest.reduce_rdms(ones, twos, structure, weights)
+        eng.set_rdms(D_sp, G_sp)
+        return eng
+
+    # -- methods of the reference --------------------------------------------------------------
+    def orth(self, V: torch.Tensor) -> torch.Tensor:
+        """orth(V) = V (V^T V)^(-1/2) (pupo.py:70-83), computed by the CUDA retraction kernel."""
+        dev = self._torch_device()
+        eng = OrbitalEngine(V.shape[0], V.shape[1], device=dev)
+        try:
+            return eng.orth(V.to(dev)).clone()
+        finally:
+            eng.close()
+
+    def _bound_problem(self, func):
+        """Recover (fun, oneRDM, twoRDM, h, g) from the functools.partial the reference builds
+        (pupo.py:176)."""
+        kw = getattr(func, "keywords", None)
+        if not kw or not all(k in kw for k in ("oneRDM", "twoRDM", "one_body_integrals",
+                                                "two_body_integrals")):
+            raise TypeError("func must be functools.partial(fun, oneRDM=..., twoRDM=..., "
+                            "one_body_integrals=..., two_body_integrals=...)")
+        return func.func, kw["oneRDM"], kw["twoRDM"], kw["one_body_integrals"], \
+            kw["two_body_integrals"]
+
+    def compute_rotated_energy_automatic_gradient(self, partial_unitary: torch.Tensor,
+                                                  func: Callable) -> torch.Tensor:
+        """dE/dU at `partial_unitary` (pupo.py:85-103) by the analytic one-pass CUDA gradient."""
+        fun, d, g2, h, g = self._bound_problem(func)
+        eng = self._prepare(fun, d, g2, h, g, partial_unitary.shape[1])
+        return eng.energy_grad(partial_unitary)[1]
+
+    def compute_rotated_energy_gradient(self, partial_unitary: torch.Tensor,
+                                        func: Callable) -> torch.Tensor:
+        """Central finite-difference gradient, step 1e-8 (pupo.py:105-127), each of the 2*M*N
+        energies evaluated by the CUDA path."""
+        fun, d, g2, h, g = self._bound_problem(func)
+        eng = self._prepare(fun, d, g2, h, g, partial_unitary.shape[1])
+        U = partial_unitary.detach().to('cpu').numpy().astype(np.float64)
+        out = np.empty_like(U)
+        step = 10 ** -8
+        for i in range(U.shape[0]):
+            for j in range(U.shape[1]):
+                up, um = U.copy(), U.copy()
+                up[i, j] += step
+                um[i, j] -= step
+                out[i, j] = (eng.energy_grad_host(up)[0] - eng.energy_grad_host(um)[0]) / (2 * step)
+        return torch.from_numpy(out).to(self._torch_device())
+
+    def compute_updated_partial_unitary(self, iteration_number: int,
+                                        current_partial_unitary: torch.Tensor,
+                                        previous_partial_unitary: torch.Tensor,
+                                        current_rotated_energy_gradient: torch.Tensor,
+                                        previous_rotated_energy_gradient: torch.Tensor
+                                        ) -> torch.Tensor:
+        """BB step size update + retraction (pupo.py:129-159); mutates BBstepsize like the
+        reference."""
+        dev = self._torch_device()
+        M, N = current_partial_unitary.shape
+        eng = OrbitalEngine(M, N, device=dev)
+        try:
+            U_next, step = eng.bb_update(iteration_number, current_partial_unitary,
+                                         previous_partial_unitary, current_rotated_energy_gradient,
+                                         previous_rotated_energy_gradient, float(self._BBstepsize))
+            self._BBstepsize = step
+            return U_next.clone()
+        finally:
+            eng.close()
+
+    def compute_optimal_rotation(self, fun: Callable,
+                                 initial_partial_unitary: torch.Tensor,
+                                 oneRDM: torch.Tensor,
+                                 twoRDM: torch.Tensor,
+                                 one_body_integrals: torch.Tensor,
+                                 two_body_integrals: torch.Tensor) -> Tuple[torch.Tensor, float]:
+        """The inner loop (pupo.py:161-350).  Returns (optimal_partial_unitary on the CPU,
+        energy as a 0-dim float64 tensor = the reference's P4_array[0])."""
+        M, N = initial_partial_unitary.shape
+        eng = self._prepare(fun, oneRDM, twoRDM, one_body_integrals, two_body_integrals, N)
+        if eng.M_user != M:
+            raise ValueError(f"initial_partial_unitary has {M} rows, integrals have {eng.M_user}")
+        U0 = initial_partial_unitary.detach().to('cpu').to(torch.float64).numpy()
+        if self.gradient_method == 'finite_difference':
+            return self._optimal_rotation_finite_difference(eng, U0)
+        res = eng.optimize(U0, float(self._BBstepsize), float(self.stopping_tolerance),
+                           int(self.maxiter), float(self.decay_factor))
+        self._BBstepsize = res["stepsize"]
+        self.last_result = {"n_iter": res["n_iter"], "E_hist": res["E_hist"][:res["n_iter"] + 1]}
+        if self._callback is not None:
+            hist, K = res["E_hist"], res["n_iter"]
+            for k in range(min(3, K + 1)):            # pupo.py:193-194, 226-227, 260-261
+                self._callback(k, float(hist[k]))
+            for k in range(3, K):                     # loop body reports the previous energy (:313)
+                self._callback(k, float(hist[k - 1]))
+        U = torch.from_numpy(res["U"])
+        return U, torch.tensor(res["energy"], dtype=torch.float64)
+
+    def _optimal_rotation_finite_difference(self, eng: OrbitalEngine, U0: np.ndarray):
+        """gradient_method='finite_difference' parity mode: the reference's driver with the
+        finite-difference gradient; energies from the CUDA path, loop on the host."""
+        step = 10 ** -8
+
+        def energy(U):
+            return eng.energy_grad_host(U)[0]
+
+        def grad(U):
+            out = np.empty_like(U)
+            for i in range(U.shape[0]):
+                for j in range(U.shape[1]):
+                    up, um = U.copy(), U.copy()
+                    up[i, j] += step
+                    um[i, j] -= step
+                    out[i, j] = (energy(up) - energy(um)) / (2 * step)
+            return out
+
+        dev = eng.device
+        tol, d = self.stopping_tolerance, self.decay_factor
+        P4, St = [None, None, None], [None, 1.5 * tol]
+        U_cur, U_prev, G_cur, G_prev = U0.copy(), None, None, None
+        k = 0
+
+        def advance():
+            nonlocal U_cur, U_prev, G_cur, G_prev, k
+            t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            U_new, bb = eng.bb_update(k, t(U_cur), t(U_prev), t(G_cur), t(G_prev),
+                                      float(self._BBstepsize))
+            self._BBstepsize = bb
+            U_new = U_new.cpu().numpy()
+            G_new = grad(U_new)
+            U_prev, G_prev, U_cur, G_cur = U_cur, G_cur, U_new, G_new
+            k += 1
+
+        cb = self._callback if self._callback is not None else (lambda *_: None)
+        P4[2] = energy(U_cur); cb(k, P4[2])
+        G_cur = grad(U_cur)
+        advance()
+        P4[1] = energy(U_cur); cb(k, P4[1])
+        St[0] = (1 - d) * abs(P4[1] - P4[2]) + d * St[1]
+        advance()
+        P4[0] = energy(U_cur); cb(k, P4[0])
+        St = [St[1], St[0]]
+        St[0] = (1 - d) * abs(P4[0] - P4[1]) + d * St[1]
+        advance()
+        while St[0] > tol and k <= self.maxiter:
+            P4 = [energy(U_cur), P4[0], P4[1]]
+            cb(k, P4[1])
+            St = [St[1], St[0]]
+            St[0] = (1 - d) * abs(P4[1] - P4[2]) + d * St[1]
+            advance()
+        self.last_result = {"n_iter": k}
+        return torch.from_numpy(U_cur), torch.tensor(P4[0], dtype=torch.float64)

@@ -1,0 +1,106 @@
+"""Freeze golden vectors from the LIVE reference implementation (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+For every case the inputs are seeded synthetic tensors (esoo_b200.synthetic) embedded in the
+reference's spin-orbital layout; the outputs come from the unmodified reference code loaded from
+/root/reference by oracle/ref_loader.py:
+    E        BaseOptOrbSolver.compute_rotated_energy            base_opt_orb_solver.py:534-582
+    grad     PartialUnitaryProjectionOptimizer.compute_rotated_energy_automatic_gradient  pupo.py:85-103
+    orth     PartialUnitaryProjectionOptimizer.orth             pupo.py:70-83
+    opt_*    PartialUnitaryProjectionOptimizer.compute_optimal_rotation  pupo.py:161-350
+Small cases store their inputs as well, so the fixtures do not depend on the generator staying
+bit-stable; large cases store input checksums.
+"""
+import os
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import esoo_b200  # noqa: E402
+from esoo_b200 import synthetic  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+torch.set_num_threads(8)
+
+CASES = [
+    # name, M, N, pattern, n_states, weights, run_opt, (bb0, tol, maxiter), store_inputs, g_scale
+    ("abba_M6_N2", 6, 2, "abba", 1, None, True, (0.05, 1e-9, 300), True, 1.0),
+    ("abab_M5_N2", 5, 2, "abab", 1, None, True, (0.05, 1e-9, 300), True, 1.0),
+    ("abba_M8_N3", 8, 3, "abba", 1, None, True, (0.02, 1e-8, 400), True, 1.0),
+    ("weighted_M6_N2_k3", 6, 2, "abba", 3, [3, 2, 1], True, (0.02, 1e-9, 300), True, 1.0),
+    ("abba_M12_N4", 12, 4, "abba", 1, None, True, (0.02, 1e-8, 500), True, 1.0),
+    ("cfg1_M28_N2", 28, 2, "abba", 1, None, True, (0.02, 1e-8, 150), False, 1.0),
+    ("cfg3_M20_N2_k3", 20, 2, "abba", 3, [3, 2, 1], True, (0.02, 1e-8, 150), False, 1.0),
+    ("cfg2_M56_N4", 56, 4, "abba", 1, None, False, None, False, 1.0),
+]
+
+
+def build_inputs(M, N, pattern, n_states, seed_shift=0, g_scale=1.0):
+    h = synthetic.h_spatial(M, synthetic.SEED_H + seed_shift)
+    g = synthetic.eri_spatial(M, synthetic.SEED_ERI + seed_shift, scale=g_scale)
+    hs, gs = synthetic.spin_orbital_integrals(h, g, pattern)
+    Ds, Gs = [], []
+    for n in range(n_states):
+        D, G = synthetic.rdms_spin(N, synthetic.SEED_RDM + seed_shift + 17 * n)
+        Ds.append(D)
+        Gs.append(G)
+    U0 = synthetic.random_partial_unitary(M, N, synthetic.SEED_U + seed_shift)
+    return hs, gs, Ds, Gs, U0
+
+
+def main():
+    Pupo, _ = ref_loader.load_reference()
+    for (name, M, N, pattern, k, weights, run_opt, optp, store, g_scale) in CASES:
+        hs, gs, Ds, Gs, U0 = build_inputs(M, N, pattern, k, g_scale=g_scale)
+        solver = ref_loader.make_solver(True, weights)
+        if weights is None:
+            fun, d_arg, g_arg = solver.compute_rotated_energy, Ds[0], Gs[0]
+        else:
+            fun, d_arg, g_arg = solver.compute_rotated_weighted_energy_sum, Ds, Gs
+        obj = partial(fun, oneRDM=d_arg, twoRDM=g_arg, one_body_integrals=hs,
+                      two_body_integrals=gs)
+        opt = Pupo(initial_BBstepsize=0.1, stopping_tolerance=1e-6, maxiter=10)
+        E = float(obj(partial_unitary=U0.clone()))
+        grad = opt.compute_rotated_energy_automatic_gradient(U0.clone(), obj).numpy()
+        V = U0 + 0.3 * synthetic.random_partial_unitary(M, N, 99)
+        orthV = opt.orth(V).numpy()
+        out = {"M": M, "N": N, "pattern": pattern, "n_states": k,
+               "weights": np.array(weights if weights else [1.0], dtype=np.float64),
+               "E": E, "grad": grad, "V": V.numpy(), "orthV": orthV, "U0": U0.numpy(),
+               "checksum_g": float(gs.sum()), "checksum_h": float(hs.sum()),
+               "checksum_G": float(sum(float(G.sum()) for G in Gs))}
+        if store:
+            out["h_spin"] = hs.numpy()
+            out["g_spin"] = gs.numpy()
+            for n in range(k):
+                out[f"D_spin_{n}"] = Ds[n].numpy()
+                out[f"G_spin_{n}"] = Gs[n].numpy()
+        if run_opt:
+            bb0, tol, maxiter = optp
+            calls = []
+            o2 = Pupo(initial_BBstepsize=bb0, stopping_tolerance=tol, maxiter=maxiter,
+                      callback=lambda it, e: calls.append((it, e)))
+            U_fin, E_fin = o2.compute_optimal_rotation(
+                fun=fun, initial_partial_unitary=U0.clone(), oneRDM=d_arg, twoRDM=g_arg,
+                one_body_integrals=hs, two_body_integrals=gs)
+            out.update({"opt_bb0": bb0, "opt_tol": tol, "opt_maxiter": maxiter,
+                        "opt_U": U_fin.numpy(), "opt_E": float(E_fin),
+                        "opt_calls_it": np.array([c[0] for c in calls], dtype=np.int64),
+                        "opt_calls_E": np.array([c[1] for c in calls], dtype=np.float64),
+                        "opt_stepsize": float(o2.BBstepsize)})
+            print(f"{name}: E={E:.12f} opt_E={float(E_fin):.12f} callbacks={len(calls)} "
+                  f"last_it={calls[-1][0]}")
+        else:
+            print(f"{name}: E={E:.12f}")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,374 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI of
+liboo_b200.so, against (a) golden vectors frozen from the live reference, (b) the numpy oracle on
+seeded inputs, (c) size-independent properties at the BASELINE.json size (M=256, N=16).
+
+Tolerances are the ones BASELINE.json's north_star states:
+    |dE| <= 1e-10 Ha per evaluation, relative dE/dU error <= 1e-9, final energies within 1e-8 Ha.
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from conftest import golden_inputs, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-10
+G_RTOL = 1e-9
+EFINAL_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests (no CPU fallback exists)")
+    return torch
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+class _Solver:
+    """Stand-in for the reference's BaseOptOrbSolver / OptOrbEigensolver: the optimiser only needs
+    the bound method's name and `weight_vector`."""
+
+    def __init__(self, weights=None):
+        self.wavefunction_real = True
+        if weights is not None:
+            self.weight_vector = list(weights)
+
+    def compute_rotated_energy(self, *a, **k):
+        raise AssertionError("the CUDA optimiser must not call the Python objective")
+
+    def compute_rotated_weighted_energy_sum(self, *a, **k):
+        raise AssertionError("the CUDA optimiser must not call the Python objective")
+
+
+def _fun_and_args(gold, Ds, Gs):
+    if int(gold["n_states"]) == 1:
+        return _Solver().compute_rotated_energy, Ds[0], Gs[0]
+    return _Solver(gold["weights"]).compute_rotated_weighted_energy_sum, Ds, Gs
+
+
+# --------------------------------------------------------------------------------------------
+# (a) golden vectors from the live reference
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_energy_gradient_vs_reference_golden(torch_cuda, name):
+    import esoo_b200
+    gold = load_golden(name)
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    fun, d_arg, g_arg = _fun_and_args(gold, Ds, Gs)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0")
+    obj = partial(fun, oneRDM=d_arg, twoRDM=g_arg, one_body_integrals=hs, two_body_integrals=gs)
+    grad = opt.compute_rotated_energy_automatic_gradient(U0.clone(), obj).cpu().numpy()
+    assert _rel(grad, gold["grad"]) <= G_RTOL
+    eng = opt._prepare(fun, d_arg, g_arg, hs, gs, U0.shape[1])
+    E, _ = eng.energy_grad_host(U0.numpy())
+    assert abs(E - float(gold["E"])) <= E_TOL
+    esoo_b200.clear_engine_cache()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_orth_vs_reference_golden(torch_cuda, name):
+    import esoo_b200
+    torch = torch_cuda
+    gold = load_golden(name)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0")
+    out = opt.orth(torch.from_numpy(gold["V"])).cpu().numpy()
+    assert np.max(np.abs(out - gold["orthV"])) <= 1e-12
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "opt_E" in load_golden(n)])
+def test_optimal_rotation_vs_reference_golden(torch_cuda, name):
+    """Whole inner loop on the device: callbacks, iteration count, final U and energy."""
+    import esoo_b200
+    gold = load_golden(name)
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    fun, d_arg, g_arg = _fun_and_args(gold, Ds, Gs)
+    calls = []
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(
+        float(gold["opt_bb0"]), float(gold["opt_tol"]), int(gold["opt_maxiter"]),
+        callback=lambda it, e: calls.append((it, e)), device="cuda:0")
+    U, E = opt.compute_optimal_rotation(fun=fun, initial_partial_unitary=U0.clone(),
+                                        oneRDM=d_arg, twoRDM=g_arg, one_body_integrals=hs,
+                                        two_body_integrals=gs)
+    assert U.device.type == "cpu" and U.dtype == torch_cuda.float64 and E.dim() == 0
+    assert abs(float(E) - float(gold["opt_E"])) <= EFINAL_TOL
+    assert [c[0] for c in calls] == list(gold["opt_calls_it"])
+    assert np.max(np.abs(np.array([c[1] for c in calls]) - gold["opt_calls_E"])) <= 1e-7
+    assert np.max(np.abs(U.numpy() - gold["opt_U"])) <= 1e-5
+    UtU = U.numpy().T @ U.numpy()
+    assert np.max(np.abs(UtU - np.eye(U.shape[1]))) <= 1e-12
+    esoo_b200.clear_engine_cache()
+
+
+# --------------------------------------------------------------------------------------------
+# (b) numpy oracle on seeded inputs: every kernel template, padding, multi-pass, sharding
+# --------------------------------------------------------------------------------------------
+def _spatial_case(torch, M, N, seed=0):
+    from esoo_b200 import synthetic
+    h = synthetic.h_spatial(M, synthetic.SEED_H + seed)
+    g = synthetic.eri_spatial(M, synthetic.SEED_ERI + seed)
+    D, G = synthetic.rdms_spatial(N, synthetic.SEED_RDM + seed)
+    U = synthetic.random_partial_unitary(M, N, synthetic.SEED_U + seed)
+    return h, g, D, G, U
+
+
+@pytest.mark.parametrize("M,N", [(8, 1), (10, 2), (16, 8), (23, 5), (40, 9), (48, 16), (36, 17),
+                                 (56, 24), (40, 25), (64, 32), (57, 32)])
+def test_energy_gradient_vs_oracle(torch_cuda, M, N):
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=M + N)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    E, grad = eng.energy_grad(U)
+    E_ref = onp.rotated_energy_spatial(U.numpy(), D.numpy(), G.numpy(), h.numpy(), g.numpy())
+    g_ref = onp.rotated_energy_grad_spatial(U.numpy(), D.numpy(), G.numpy(), h.numpy(), g.numpy())
+    assert abs(float(E) - E_ref) <= E_TOL * max(1.0, abs(E_ref))
+    assert _rel(grad.cpu().numpy(), g_ref) <= G_RTOL
+    Eh, gh = eng.energy_grad_host(U.numpy())
+    assert Eh == float(E) and np.array_equal(gh, grad.cpu().numpy())
+    eng.close()
+
+
+def test_general_gamma_needs_only_g_symmetry(torch_cuda):
+    """A 2-RDM without any permutational symmetry: the V4 average inside the library must still
+    give the exact generic gradient because g is V4-symmetric."""
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    M, N = 20, 6
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=3)
+    gen = torch.Generator().manual_seed(5)
+    G = torch.randn(N, N, N, N, generator=gen, dtype=torch.float64)
+    D = torch.randn(N, N, generator=gen, dtype=torch.float64)
+    h = torch.randn(M, M, generator=gen, dtype=torch.float64)      # non-symmetric h as well
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    E, grad = eng.energy_grad(U)
+    E_ref = onp.rotated_energy_spatial(U.numpy(), D.numpy(), G.numpy(), h.numpy(), g.numpy())
+    g_ref = onp.rotated_energy_grad_spatial(U.numpy(), D.numpy(), G.numpy(), h.numpy(), g.numpy())
+    assert abs(float(E) - E_ref) <= E_TOL * max(1.0, abs(E_ref))
+    assert _rel(grad.cpu().numpy(), g_ref) <= G_RTOL
+    eng.close()
+
+
+def test_nonsymmetric_integrals_are_rejected(torch_cuda):
+    import esoo_b200
+    torch = torch_cuda
+    M, N = 8, 2
+    g = torch.randn(M, M, M, M, dtype=torch.float64)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        eng.set_integrals(torch.eye(M, dtype=torch.float64), g)
+    eng.close()
+
+
+@pytest.mark.parametrize("M,N,t0,mloc", [(272, 8, 268, 4), (400, 24, 100, 2), (264, 16, 0, 3)])
+def test_multipass_shard_vs_oracle(torch_cuda, M, N, t0, mloc):
+    """M > 256 exercises the second 256-row pass of K1 (partially filled row-blocks) on a thin
+    shard of the first index; the oracle contracts the same rows."""
+    import esoo_b200
+    from esoo_b200 import synthetic
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    h = synthetic.h_spatial(M)
+    gsh = synthetic.eri_spatial_shard(M, t0, mloc, device="cuda:0")
+    D, G = synthetic.rdms_spatial(N)
+    U = synthetic.random_partial_unitary(M, N)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0", t0=t0, mloc=mloc)
+    eng.set_integrals(h, gsh, assume_v4_symmetric=True)
+    eng.set_rdms(D, G)
+    E, grad = eng.energy_grad(U)
+    Un, Dn, Gn, hn = U.numpy(), D.numpy(), G.numpy(), h.numpy()
+    Gs = 0.25 * (Gn + Gn.transpose(1, 0, 3, 2) + Gn.transpose(2, 3, 0, 1) + Gn.transpose(3, 2, 1, 0))
+    T3 = onp._transform_last3(gsh.cpu().numpy(), Un)
+    A = np.tensordot(T3, Gs, axes=([1, 2, 3], [1, 2, 3]))
+    rows = slice(t0, t0 + mloc)
+    B1 = (hn @ Un @ Dn.T)[rows]
+    B2 = (hn.T @ Un @ Dn)[rows]
+    g_ref = 4 * A + B1 + B2
+    E_ref = float(np.sum(Un[rows] * (A + B1)))
+    out = grad.cpu().numpy()
+    assert abs(float(E) - E_ref) <= E_TOL * max(1.0, abs(E_ref))
+    assert _rel(out[rows], g_ref) <= G_RTOL
+    mask = np.ones(M, bool)
+    mask[rows] = False
+    assert np.all(out[mask] == 0.0)
+    eng.close()
+
+
+def test_two_shards_sum_to_full(torch_cuda):
+    """World-size-2 emulation on one GPU: the shard outputs add up to the unsharded result."""
+    import esoo_b200
+    torch = torch_cuda
+    M, N = 48, 8
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=1)
+    full = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    full.set_integrals(h, g)
+    full.set_rdms(D, G)
+    E, grad = full.energy_grad(U)
+    acc_E, acc_g = 0.0, torch.zeros_like(grad)
+    for rank in range(2):
+        t0, mloc = esoo_b200.shard_range(M, rank, 2)
+        eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0", t0=t0, mloc=mloc)
+        eng.set_integrals(h, g[t0:t0 + mloc], assume_v4_symmetric=True)
+        eng.set_rdms(D, G)
+        e, gr = eng.energy_grad(U)
+        acc_E += float(e)
+        acc_g += gr
+        eng.close()
+    assert abs(acc_E - float(E)) <= 1e-12 * max(1.0, abs(float(E)))
+    assert _rel(acc_g.cpu().numpy(), grad.cpu().numpy()) <= 1e-13
+    full.close()
+
+
+def test_transform_vs_oracle(torch_cuda):
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    M, N = 30, 6
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=2)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    h_rot, g_rot = eng.transform(U)
+    h_ref, g_ref = onp.rotated_integrals_spatial(U.numpy(), h.numpy(), g.numpy())
+    assert np.max(np.abs(h_rot.cpu().numpy() - h_ref)) <= 1e-11
+    assert np.max(np.abs(g_rot.cpu().numpy() - g_ref)) <= 1e-11
+    eng.close()
+
+
+@pytest.mark.parametrize("iteration", [0, 1, 2, 5])
+def test_bb_update_vs_oracle(torch_cuda, iteration):
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    M, N = 26, 7
+    gen = torch.Generator().manual_seed(iteration)
+    Uc = torch.linalg.qr(torch.randn(M, N, generator=gen, dtype=torch.float64))[0]
+    Up = torch.linalg.qr(torch.randn(M, N, generator=gen, dtype=torch.float64))[0]
+    Gc = torch.randn(M, N, generator=gen, dtype=torch.float64)
+    Gp = torch.randn(M, N, generator=gen, dtype=torch.float64)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.07, 1e-6, 10, device="cuda:0")
+    out = opt.compute_updated_partial_unitary(iteration, Uc, Up if iteration else None, Gc,
+                                              Gp if iteration else None)
+    ref, step = onp.bb_update(iteration, Uc.numpy(), Up.numpy(), Gc.numpy(), Gp.numpy(), 0.07)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-12
+    assert abs(float(opt.BBstepsize) - step) <= 1e-13 * max(1.0, abs(step))
+
+
+def test_optimize_vs_oracle_loop(torch_cuda):
+    """Device-resident loop against the oracle's restatement of pupo.py:161-350 on a spatial
+    problem no golden covers (N=9 -> NT=2 with padding)."""
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    M, N = 24, 9
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=4)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    res = eng.optimize(U.numpy(), 0.02, 1e-9, 250)
+    hn, gn, Dn, Gn = h.numpy(), g.numpy(), D.numpy(), G.numpy()
+    ref = onp.optimal_rotation(lambda X: onp.rotated_energy_spatial(X, Dn, Gn, hn, gn),
+                               lambda X: onp.rotated_energy_grad_spatial(X, Dn, Gn, hn, gn),
+                               U.numpy(), 0.02, 1e-9, 250)
+    assert res["n_iter"] == ref["n_iter"]
+    assert abs(res["energy"] - ref["energy"]) <= EFINAL_TOL
+    assert np.max(np.abs(res["U"] - ref["U"])) <= 1e-5
+    eng.close()
+
+
+def test_finite_difference_mode(torch_cuda):
+    """gradient_method='finite_difference' (pupo.py:105-127): FD gradient of the CUDA energy
+    agrees with the analytic CUDA gradient to FD accuracy."""
+    import esoo_b200
+    gold = load_golden("abba_M6_N2")
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    fun = _Solver().compute_rotated_energy
+    obj = partial(fun, oneRDM=Ds[0], twoRDM=Gs[0], one_body_integrals=hs, two_body_integrals=gs)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0",
+                                                      gradient_method="finite_difference")
+    fd = opt.compute_rotated_energy_gradient(U0.clone(), obj).cpu().numpy()
+    assert _rel(fd, gold["grad"]) <= 1e-6
+    esoo_b200.clear_engine_cache()
+
+
+def test_rejects_unknown_objective_and_complex(torch_cuda):
+    import esoo_b200
+    torch = torch_cuda
+    gold = load_golden("abba_M6_N2")
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0")
+    with pytest.raises(TypeError):
+        opt.compute_optimal_rotation(lambda **k: 0.0, U0, Ds[0], Gs[0], hs, gs)
+    with pytest.raises(NotImplementedError):
+        opt.compute_optimal_rotation(_Solver().compute_rotated_energy, U0,
+                                     Ds[0].to(torch.complex128), Gs[0].to(torch.complex128), hs, gs)
+    esoo_b200.clear_engine_cache()
+
+
+# --------------------------------------------------------------------------------------------
+# (c) BASELINE.json size: M=256, N=16 — properties that do not need a CPU answer
+# --------------------------------------------------------------------------------------------
+def test_full_size_properties(torch_cuda):
+    import esoo_b200
+    from esoo_b200 import synthetic
+    torch = torch_cuda
+    M, N = 256, 16
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 40 * (1 << 30):
+        pytest.skip("needs 40 GB of free device memory")
+    h = synthetic.h_spatial(M).cuda()
+    g = synthetic.eri_spatial(M, device="cuda:0")
+    U = synthetic.random_partial_unitary(M, N).cuda()
+    D1, G1 = synthetic.rdms_spatial(N, seed=11)
+    D2, G2 = synthetic.rdms_spatial(N, seed=12)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)                      # includes the on-device V4 symmetry verification
+    a, b = 0.7, -1.3
+    eng.set_rdms(D1, G1)
+    E1, g1 = eng.energy_grad(U)
+    eng.set_rdms(D2, G2)
+    E2, g2 = eng.energy_grad(U)
+    eng.set_rdms(a * D1 + b * D2, a * G1 + b * G2)
+    E3, g3 = eng.energy_grad(U)
+    # linearity in the RDMs (eig.py:149-169 relies on it)
+    scale = max(abs(float(E1)), abs(float(E2)), 1.0)
+    assert abs(float(E3) - (a * float(E1) + b * float(E2))) <= 1e-10 * scale
+    assert _rel(g3.cpu().numpy(), (a * g1 + b * g2).cpu().numpy()) <= 1e-11
+    # gradient = directional derivative of the energy (central difference along a random X)
+    gen = torch.Generator().manual_seed(3)
+    X = torch.randn(M, N, generator=gen, dtype=torch.float64).cuda()
+    X /= X.norm()
+    eps = 1e-4
+    Ep, _ = eng.energy_grad(U + eps * X)
+    Em, _ = eng.energy_grad(U - eps * X)
+    fd = (float(Ep) - float(Em)) / (2 * eps)
+    an = float((g3 * X).sum())
+    assert abs(fd - an) <= 1e-6 * max(1.0, abs(an))
+    # determinism: bit-identical repeat
+    E4, g4 = eng.energy_grad(U)
+    assert float(E4) == float(E3) and torch.equal(g4, g3)
+    # shard additivity at full size (8 shards, as on an 8-GPU box)
+    accE, accg = 0.0, torch.zeros_like(g3)
+    for r in range(8):
+        t0, mloc = esoo_b200.shard_range(M, r, 8)
+        sh = esoo_b200.OrbitalEngine(M, N, device="cuda:0", t0=t0, mloc=mloc)
+        sh.set_integrals(h, g[t0:t0 + mloc], assume_v4_symmetric=True)
+        sh.set_rdms(a * D1 + b * D2, a * G1 + b * G2)
+        e, gr = sh.energy_grad(U)
+        accE += float(e)
+        accg += gr
+        sh.close()
+    assert abs(accE - float(E3)) <= 1e-10 * scale
+    assert _rel(accg.cpu().numpy(), g3.cpu().numpy()) <= 1e-12
+    eng.close()

@@ -1,0 +1,254 @@
+"""CPU-only tests: C-ABI surface of the built library, host-side ingest / sharding logic, the
+world-size-2 data path over gloo, and the "fail loudly without a GPU" contract."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import esoo_b200
+    from esoo_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "oo_b200.h")).read()
+    declared = set(re.findall(r"\b(oo_[a-z0-9_]+)\s*\(", header))
+    declared -= {"oo_ctx", "oo_status"}
+    assert declared, "no declarations found in include/oo_b200.h"
+    assert os.path.isfile(_lib.LIB_PATH), "liboo_b200.so has not been built (run __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"symbols declared in the header but not exported: {missing}"
+    assert declared == set(_lib.SYMBOLS)
+    assert b"sm_100a" in _lib.load().oo_version()
+
+
+def test_no_cpu_fallback():
+    import esoo_b200
+    with pytest.raises(ValueError):
+        esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            esoo_b200.OrbitalEngine(8, 2, device="cuda:0")
+        # the C layer reports the missing device instead of computing anything
+        lib = esoo_b200._lib.load()
+        ctx = ctypes.c_void_p()
+        rc = lib.oo_create(0, 8, 2, 0, 8, ctypes.byref(ctx))
+        assert rc != 0 and lib.oo_last_error()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "electronic-structure-orbital-optimization_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_constructor_mirrors_reference_signature():
+    import inspect
+    import esoo_b200
+    sig = inspect.signature(esoo_b200.PartialUnitaryProjectionOptimizer.__init__)
+    assert list(sig.parameters)[1:] == ["initial_BBstepsize", "stopping_tolerance", "maxiter",
+                                        "callback", "decay_factor", "gradient_method", "device"]
+    o = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 7, device="cuda:1")
+    assert (o.BBstepsize, o.stopping_tolerance, o.maxiter, o.decay_factor, o.device,
+            o.gradient_method, o.callback) == (0.1, 1e-6, 7, 0.8, "cuda:1", "autograd", None)
+    import copy
+    c = copy.deepcopy(o)            # base_opt_orb_solver.py:75 deep-copies the optimiser
+    c.BBstepsize = 0.5
+    assert o.BBstepsize == 0.1
+    for m in ("orth", "compute_rotated_energy_automatic_gradient", "compute_rotated_energy_gradient",
+              "compute_updated_partial_unitary", "compute_optimal_rotation"):
+        assert callable(getattr(o, m))
+    ref_sig = ["fun", "initial_partial_unitary", "oneRDM", "twoRDM", "one_body_integrals",
+               "two_body_integrals"]
+    assert list(inspect.signature(o.compute_optimal_rotation).parameters) == ref_sig
+
+
+def test_signature_matches_live_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present on this machine")
+    import inspect
+    import esoo_b200
+    Ref, _ = ref_loader.load_reference()
+    ours = esoo_b200.PartialUnitaryProjectionOptimizer
+    for name in ("__init__", "orth", "compute_rotated_energy_automatic_gradient",
+                 "compute_rotated_energy_gradient", "compute_updated_partial_unitary",
+                 "compute_optimal_rotation"):
+        assert list(inspect.signature(getattr(ours, name)).parameters) == \
+            list(inspect.signature(getattr(Ref, name)).parameters), name
+
+
+def test_fun_identification():
+    from functools import partial
+    from esoo_b200.optimizer import _fun_identity
+
+    class S:
+        weight_vector = [2, 1]
+
+        def compute_rotated_energy(self):
+            pass
+
+        def compute_rotated_weighted_energy_sum(self):
+            pass
+
+        def other(self):
+            pass
+
+    s = S()
+    assert _fun_identity(s.compute_rotated_energy) == ("compute_rotated_energy", s)
+    assert _fun_identity(partial(s.compute_rotated_weighted_energy_sum))[0] == \
+        "compute_rotated_weighted_energy_sum"
+    with pytest.raises(TypeError):
+        _fun_identity(s.other)
+    with pytest.raises(TypeError):
+        _fun_identity(lambda: 0)
+
+
+@pytest.mark.parametrize("pattern", ["abba", "abab"])
+def test_ingest_detects_block_pattern(pattern):
+    from esoo_b200 import ingest, synthetic
+    M, N = 5, 2
+    h, g = synthetic.h_spatial(M), synthetic.eri_spatial(M)
+    hs, gs = synthetic.spin_orbital_integrals(h, g, pattern)
+    h2, g2, st = ingest.reduce_integrals(hs, gs)
+    assert torch.equal(h2, h) and torch.equal(g2, g) and len(st.blocks) == 4
+    D, G = synthetic.rdms_spin(N)
+    Dsp, Gsp = ingest.reduce_rdms(D, G, st)
+    Dref, Gref = synthetic.rdms_spatial(N, pattern=pattern)
+    assert torch.allclose(Dsp, Dref, atol=0, rtol=0) and torch.allclose(Gsp, Gref, atol=1e-15)
+    # weights: linear combination of states
+    D2, G2 = synthetic.rdms_spin(N, seed=5)
+    Dw, Gw = ingest.reduce_rdms([D, D2], [G, G2], st, [2.0, 1.0])
+    Da, Ga = ingest.reduce_rdms(D2, G2, st)
+    assert torch.allclose(Dw, 2 * Dsp + Da, atol=1e-15) and torch.allclose(Gw, 2 * Gsp + Ga, atol=1e-15)
+
+
+def test_ingest_rejects_out_of_contract_inputs():
+    from esoo_b200 import ingest, synthetic
+    M, N = 4, 2
+    h, g = synthetic.h_spatial(M), synthetic.eri_spatial(M)
+    hs, gs = synthetic.spin_orbital_integrals(h, g)
+    bad = gs.clone()
+    bad[:M, :M, :M, :M] = 2 * g                       # unrestricted: alpha-alpha block differs
+    with pytest.raises(NotImplementedError):
+        ingest.reduce_integrals(hs, bad)
+    hb = hs.clone()
+    hb[0, M] = 1.0                                    # alpha-beta coupling
+    with pytest.raises(NotImplementedError):
+        ingest.reduce_integrals(hb, gs)
+    with pytest.raises(TypeError):
+        ingest.reduce_integrals(hs.float(), gs.float())
+    _, _, st = ingest.reduce_integrals(hs, gs)
+    D, G = synthetic.rdms_spin(N)
+    with pytest.raises(NotImplementedError):
+        ingest.reduce_rdms(D.to(torch.complex128), G.to(torch.complex128), st)
+    with pytest.raises(ValueError):
+        ingest.reduce_rdms([D, D], [G, G], st, [1.0])
+
+
+def test_shard_range_partitions():
+    from esoo_b200 import shard_range
+    for M, W in [(256, 8), (400, 8), (10, 4), (7, 7), (28, 1), (110, 3)]:
+        rows = []
+        for r in range(W):
+            t0, n = shard_range(M, r, W)
+            assert n >= 1
+            rows += list(range(t0, t0 + n))
+        assert rows == list(range(M))
+    with pytest.raises(ValueError):
+        shard_range(3, 0, 4)
+
+
+def test_synthetic_eri_is_v4_symmetric_and_shards_agree():
+    from esoo_b200 import synthetic
+    M = 9
+    g = synthetic.eri_spatial(M)
+    for perm in [(1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 1, 0)]:
+        assert torch.allclose(g, g.permute(*perm), atol=1e-15)
+    sh = synthetic.eri_spatial_shard(M, 3, 4)
+    assert torch.equal(sh, g[3:7])
+    U = synthetic.random_partial_unitary(12, 5)
+    assert torch.allclose(U.T @ U, torch.eye(5, dtype=torch.float64), atol=1e-14)
+    D, G = synthetic.rdms_spin(3)
+    assert abs(float(torch.trace(D)) - 2.0) < 1e-12           # 1 alpha + 1 beta electron
+    assert torch.allclose(G, -G.permute(1, 0, 2, 3), atol=1e-15)  # antisymmetry in (p,q)
+
+
+# ------------------------------------------------------------------------------------------------
+# world-size-2 data path on CPU (gloo): shard -> partial (E, grad rows) -> all-reduce == full
+# ------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import esoo_b200
+    from esoo_b200 import synthetic, distributed
+    from oracle import oracle_np as onp
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    M, N = 11, 3
+    h, g = synthetic.h_spatial(M).numpy(), synthetic.eri_spatial(M).numpy()
+    D, G = (t.numpy() for t in synthetic.rdms_spatial(N))
+    U = synthetic.random_partial_unitary(M, N).numpy()
+    t0, mloc = distributed.shard_range(M, rank, world)
+    rows = slice(t0, t0 + mloc)
+    Gs = 0.25 * (G + G.transpose(1, 0, 3, 2) + G.transpose(2, 3, 0, 1) + G.transpose(3, 2, 1, 0))
+    T3 = onp._transform_last3(g[rows], U)
+    A = np.tensordot(T3, Gs, axes=([1, 2, 3], [1, 2, 3]))
+    B1, B2 = (h @ U @ D.T)[rows], (h.T @ U @ D)[rows]
+    buf = np.zeros(M * N + 1)
+    buf[:M * N].reshape(M, N)[rows] = 4 * A + B1 + B2
+    buf[M * N] = np.sum(U[rows] * (A + B1))
+    t = torch.from_numpy(buf)
+    dist.all_reduce(t)                                   # the (M*N+1)-double sum all-reduce
+
+    class FakeEngine:                                    # attach_nccl's bootstrap, without NCCL
+        device = torch.device("cpu")
+        got = None
+
+        @staticmethod
+        def nccl_unique_id():
+            return bytes(range(128))
+
+        def attach_comm(self, uid, r, w):
+            FakeEngine.got = (uid, r, w)
+
+    fe = FakeEngine()
+    distributed.attach_nccl(fe)
+    E_ref = onp.rotated_energy_spatial(U, D, G, h, g)
+    g_ref = onp.rotated_energy_grad_spatial(U, D, G, h, g)
+    ok = abs(t[M * N].item() - E_ref) < 1e-12 and \
+        np.max(np.abs(t[:M * N].numpy().reshape(M, N) - g_ref)) < 1e-12 and \
+        FakeEngine.got == (bytes(range(128)), rank, world)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
