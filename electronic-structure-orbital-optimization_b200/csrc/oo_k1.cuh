@@ -17,8 +17,8 @@
 //                                                 fragments with a permuted k order), B = U^T (smem)
 // Work decomposition: persistent CTAs (one per SM), slabs dealt round-robin; inside a CTA one TMA
 // producer warp and 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
-// the current 256-row pass and all of its columns, so the second contraction costs 8*NT^2/NT... a
-// fixed N/M fraction of the first.
+// the current 256-row pass and all of its columns, so the second contraction costs a fixed N/M
+// fraction of the first.
 #pragma once
 #include "oo_common.cuh"
 
@@ -36,7 +36,9 @@ struct K1Params {
   double* Y;             // [nslab][Np][Np], element (l,k) of slab = Y_tq[k][l]
   const int* done_flag;  // optional: non-zero => kernel is a no-op (optimiser already stopped)
   int M, N;
-  int nslab;             // number of (t,q) slabs owned by this GPU (= Mloc * M)
+  const int* slab_coord; // optional: slab i lives at tensor coordinate slab_coord[i] = tl*M + q
+                         // (pair-symmetric mode: only one of (t,q)/(q,t) is streamed); NULL = i
+  int nslab;             // number of (t,q) slabs this GPU streams (dense: Mloc * M)
   int nstage;            // TMA ring depth
   int Mk;                // M rounded up to a multiple of K1_KC
   int upitch;            // row pitch (doubles) of the transposed U copy in smem: Mk + 8
@@ -120,12 +122,13 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+        const int coord = p.slab_coord ? __ldg(p.slab_coord + slab) : slab;
         for (int pass = 0; pass < npass; ++pass) {
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(empty_base + 8u * stage, phase ^ 1u);
             mbar_arrive_expect_tx(full_base + 8u * stage, K1_STAGE_BYTES);
             tma_load_3d(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
-                        pass * K1_ROWS, slab, full_base + 8u * stage);
+                        pass * K1_ROWS, coord, full_base + 8u * stage);
             if (++stage == p.nstage) {
               stage = 0;
               phase ^= 1u;
