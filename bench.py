@@ -39,12 +39,12 @@ def _load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _load_traffic(M, N, mloc):
+def _load_traffic(M, N, mloc, slabs):
     """Per-launch DRAM bytes of K1 from the committed ncu capture, if it is for this shape."""
     try:
         with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
             t = json.load(f)
-        if (t["M"], t["N"], t["mloc"]) == (M, N, mloc):
+        if (t["M"], t["N"], t["mloc"], t.get("slabs", mloc * M)) == (M, N, mloc, slabs):
             return float(t["dram_bytes_per_launch"])
     except Exception:
         pass
@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--M", type=int, default=M_BENCH)
     ap.add_argument("--N", type=int, default=N_BENCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense", action="store_true",
+                    help="stream every slab of the shard instead of one per (t,q)/(q,t) pair")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -196,6 +198,8 @@ def main():
         eng.set_integrals(h, g, assume_v4_symmetric=True)   # symmetric by construction
         esoo_b200.attach_nccl(eng)
     eng.set_rdms(D, G)
+    eng.set_pair_symmetry(not args.dense)
+    slabs = eng.streamed_slabs()
     stream = torch.cuda.Stream(device=dev)
     eng.use_stream(stream)
 
@@ -270,11 +274,13 @@ def main():
     if rank == 0:
         hbm_peak, peak_src = _load_peaks()
         dmma, dfma, stream_read = esoo_b200.measure_peaks(local, 4 << 30)
-        alg_bytes = 8.0 * mloc * M ** 3
-        alg_flops = 2.0 * mloc * M ** 3 * N + 2.0 * mloc * M ** 2 * N ** 2
+        # algorithmic work of K1 = the M x M slabs it streams (dense: all mloc*M of the shard;
+        # pair-symmetric: one of every pair (t,q)/(q,t), Y[q,t] = Y[t,q]^T)
+        alg_bytes = 8.0 * slabs * M ** 2
+        alg_flops = slabs * (2.0 * M ** 2 * N + 2.0 * M * N ** 2)
         ach_gbs = alg_bytes / (k1_avg * 1e-3) / 1e9
         ach_tf = alg_flops / (k1_avg * 1e-3) / 1e12
-        traffic = _load_traffic(M, N, mloc)
+        traffic = _load_traffic(M, N, mloc, slabs)
         line = {
             "metric": METRIC if (M, N) == (M_BENCH, N_BENCH) else
             f"orbital-opt energy+grad evals/sec at M={M},N={N} (FP64)",
@@ -283,7 +289,11 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if (M, N) == (M_BENCH, N_BENCH) else
                        f"synthetic 8-fold-symmetric ERI M={M}, N={N}",
-                       "M": M, "N": N, "eri_bytes_per_gpu": alg_bytes,
+                       "M": M, "N": N, "eri_shard_bytes_per_gpu": 8.0 * mloc * M ** 3,
+                       "slab_mode": "dense" if args.dense else
+                       "pair-symmetric (one slab per (t,q)/(q,t) pair, symmetry verified on device)",
+                       "slabs_streamed_per_eval_per_gpu": slabs,
+                       "eri_bytes_streamed_per_eval_per_gpu": alg_bytes,
                        "sharding": f"ERI first index over {world} GPU(s), rows/GPU={mloc}",
                        "cache": "ERI shard (>=4.3 GB) is larger than the 126 MB L2 and a fresh U "
                                 "is used every step; no explicit L2 flush"},

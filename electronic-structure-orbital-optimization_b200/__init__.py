@@ -3,7 +3,7 @@ Barzilai-Borwein step) behind the reference's PartialUnitaryProjectionOptimizer 
 
 The numerical work is done by hand-written sm_100a CUDA kernels in liboo_b200.so (C ABI:
 include/oo_b200.h); this package is the host-side mirror of the reference interface."""
-from . import _lib, ingest, synthetic
+from . import _lib, distributed, ingest, synthetic
 from .engine import OrbitalEngine, measure_peaks
 from .optimizer import PartialUnitaryProjectionOptimizer, clear_engine_cache
 from .distributed import shard_range, attach_nccl

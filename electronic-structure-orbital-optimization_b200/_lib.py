@@ -16,7 +16,7 @@ SYMBOLS = [
     "oo_synchronize", "oo_set_integrals", "oo_check_v4_symmetry", "oo_set_rdms", "oo_energy_grad",
     "oo_energy_grad_host", "oo_transform", "oo_orth", "oo_bb_update", "oo_optimize",
     "oo_nccl_unique_id", "oo_comm_init", "oo_allreduce", "oo_set_timing", "oo_last_timing",
-    "oo_launch_count", "oo_measure_peaks",
+    "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -85,6 +85,8 @@ def load() -> C.CDLL:
     lib.oo_launch_count.argtypes = [vp]
     lib.oo_launch_count.restype = C.c_longlong
     lib.oo_measure_peaks.argtypes = [C.c_int, sz, dp]
+    lib.oo_set_pair_symmetry.argtypes = [vp, C.c_int]
+    lib.oo_streamed_slabs.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("oo_device_count",):

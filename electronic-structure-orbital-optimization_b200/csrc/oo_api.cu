@@ -117,6 +117,11 @@ struct oo_ctx {
          *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr;
   int hist_cap = 0;
   unsigned int* counter = nullptr;
+  // pair-symmetric slab selection (see oo_k2.cuh)
+  int* slab_coord = nullptr;    // [nsel] tensor coordinate tl*M+q of the i-th streamed slab
+  int* idxmap = nullptr;        // [mloc][M] slab index or -1
+  int nsel = 0;
+  bool pair_sym = true;
   OptState* state = nullptr;
   // pinned host staging
   double* pin = nullptr;        // M*N+1 doubles
@@ -177,7 +182,8 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag) {
   p.done_flag = done_flag;
   p.M = c->M;
   p.N = c->N;
-  p.nslab = c->mloc * c->M;
+  p.slab_coord = c->pair_sym ? c->slab_coord : nullptr;
+  p.nslab = c->pair_sym ? c->nsel : c->mloc * c->M;
   p.nstage = c->nstage;
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
@@ -215,9 +221,20 @@ int launch_qc_t(oo_ctx* c, const double* U, const int* done_flag) {
     attr_set[c->device & 7] = true;
   }
   if (smem > 227 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
-  dim3 grid(c->mloc, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
-  k_qcontract<NT><<<grid, QC_ECHUNK * QC_QGROUPS, smem, c->stream>>>(c->Y, U, c->T3, c->M, c->N,
-                                                                    done_flag);
+  QCParams qp;
+  qp.Y = c->Y;
+  qp.U = U;
+  qp.T3 = c->T3;
+  qp.idxmap = c->pair_sym ? c->idxmap : nullptr;
+  qp.done_flag = done_flag;
+  qp.M = c->M;
+  qp.N = c->N;
+  qp.t0 = c->t0;
+  qp.mloc = c->mloc;
+  qp.row0 = c->pair_sym ? 0 : c->t0;
+  qp.nrows = c->pair_sym ? c->M : c->mloc;
+  dim3 grid(qp.nrows, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
+  k_qcontract<NT><<<grid, QC_ECHUNK * QC_QGROUPS, smem, c->stream>>>(qp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
@@ -246,7 +263,7 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) 
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
   {
     const int L = c->Np * c->Np * c->Np;
-    dim3 grid(c->mloc, (c->N + GC_AGROUP - 1) / GC_AGROUP);
+    dim3 grid(c->pair_sym ? c->M : c->mloc, (c->N + GC_AGROUP - 1) / GC_AGROUP);
     k_gamma_contract<<<grid, 256, 0, c->stream>>>(c->T3, c->Gp, c->A, c->N, L, done_flag);
     CU_TRY(cudaGetLastError());
     c->launches++;
@@ -269,9 +286,11 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) 
     fp.M = c->M;
     fp.N = c->N;
     fp.t0 = c->t0;
-    fp.Mloc = c->mloc;
+    fp.mloc = c->mloc;
+    fp.row0 = c->pair_sym ? 0 : c->t0;
+    fp.nrows = c->pair_sym ? c->M : c->mloc;
     fp.two_body_grad_factor = 4.0;
-    k_finalize<<<c->mloc, 128, 0, c->stream>>>(fp);
+    k_finalize<<<fp.nrows, 128, 0, c->stream>>>(fp);
     CU_TRY(cudaGetLastError());
     c->launches++;
   }
@@ -358,19 +377,37 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(double));
   };
   A(&c->Y, (size_t)mloc * M * Np2);
-  A(&c->T3, (size_t)mloc * c->Np * Np2);
+  A(&c->T3, (size_t)M * c->Np * Np2);
   A(&c->Gp, (size_t)N * c->Np * Np2);
   A(&c->D, (size_t)N * N);
-  A(&c->A, (size_t)mloc * N);
+  A(&c->A, (size_t)M * N);
   A(&c->UD, MN);
   A(&c->UDt, MN);
-  A(&c->rowE, mloc);
+  A(&c->rowE, M);
   A(&c->out, MN + 1);
   A(&c->Ucur, MN);
   A(&c->Uprev, MN);
   A(&c->Gprev, MN);
   A(&c->Vtmp, MN);
   A(&c->alpha_tmp, 4);
+  {
+    // slab tables of the pair-symmetric mode
+    std::vector<int> coord, idx((size_t)mloc * M, -1);
+    coord.reserve((size_t)mloc * (M / 2 + 1));
+    for (int tl = 0; tl < mloc; ++tl)
+      for (int q = 0; q < M; ++q)
+        if (pair_selected(t0 + tl, q)) {
+          idx[(size_t)tl * M + q] = (int)coord.size();
+          coord.push_back(tl * M + q);
+        }
+    c->nsel = (int)coord.size();
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->slab_coord, coord.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->idxmap, idx.size() * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(c->slab_coord, coord.data(), coord.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(c->idxmap, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc((void**)&c->counter, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(c->counter, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&c->state, sizeof(OptState));
@@ -403,6 +440,8 @@ int oo_destroy(oo_ctx* c) {
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (c->counter) cudaFree(c->counter);
+  if (c->slab_coord) cudaFree(c->slab_coord);
+  if (c->idxmap) cudaFree(c->idxmap);
   if (c->state) cudaFree(c->state);
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_state) cudaFreeHost(c->pin_state);
@@ -514,8 +553,9 @@ int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_ro
   if (g_rot_dev) {
     if ((rc = launch_k1(c, U_dev, nullptr))) return rc;
     if ((rc = launch_qc(c, U_dev, nullptr))) return rc;
-    k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np, c->t0,
-                                                   c->mloc);
+    k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np,
+                                                   c->pair_sym ? 0 : c->t0,
+                                                   c->pair_sym ? c->M : c->mloc);
     CU_TRY(cudaGetLastError());
     c->launches++;
   }
@@ -695,6 +735,21 @@ int oo_allreduce(oo_ctx* c, double* buf_dev, size_t count) {
   if (!c->comm) return fail(OO_ERR_STATE, "no communicator attached (oo_comm_init)");
   CU_TRY(cudaSetDevice(c->device));
   return do_allreduce(c, buf_dev, count);
+}
+
+int oo_set_pair_symmetry(oo_ctx* c, int enable) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->pair_sym = enable != 0;
+  // rows outside the shard are only written in pair-symmetric mode: start from zero again
+  CU_TRY(cudaMemsetAsync(c->out, 0, ((size_t)c->M * c->N + 1) * sizeof(double), c->stream));
+  return OO_OK;
+}
+
+int oo_streamed_slabs(oo_ctx* c) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  return c->pair_sym ? c->nsel : c->mloc * c->M;
 }
 
 int oo_set_timing(oo_ctx* c, int enable) {

@@ -60,20 +60,71 @@ struct K1Frag {
   double u[NT][2];     // A operand: U[s][l]
 };
 
-// 2 k4-steps x RB row-blocks x NT column tiles of DMMA on one fragment set.  FULL = every
-// row-block of this warp is inside the slab (no predicates, no WARPSYNC in the hot loop).
-template <int NT, bool FULL>
-__device__ __forceinline__ void k1_mma_chunk(double (&acc)[K1_RB][NT][2], const K1Frag<NT>& f,
-                                             const bool (&act)[K1_RB]) {
+// 2 k4-steps x NACT row-blocks x NT column tiles of DMMA on one fragment set.  NACT = number of
+// this warp's row-blocks that lie inside the slab in the current pass (always a prefix).  It is
+// a template parameter reached through a warp-uniform switch: a predicated-off DMMA still
+// occupies the tensor pipe (measured: profiles/r01_ncu_summary.md), a branch does not.
+template <int NT, int NACT>
+__device__ __forceinline__ void k1_mma_chunk_n(double (&acc)[K1_RB][NT][2], const K1Frag<NT>& f) {
 #pragma unroll
   for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int rb = 0; rb < K1_RB; ++rb)
-      if (FULL || act[rb]) {
+    for (int rb = 0; rb < NACT; ++rb)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-          dmma884(acc[rb][nt][0], acc[rb][nt][1], f.u[nt][j], f.g[rb][j]);
+      for (int nt = 0; nt < NT; ++nt)
+        dmma884(acc[rb][nt][0], acc[rb][nt][1], f.u[nt][j], f.g[rb][j]);
+}
+
+template <int NT>
+__device__ __forceinline__ void k1_mma_chunk(double (&acc)[K1_RB][NT][2], const K1Frag<NT>& f,
+                                             int nact) {
+  static_assert(K1_RB == 4, "switch below enumerates 0..4 active row-blocks");
+  switch (nact) {
+    case 4: k1_mma_chunk_n<NT, 4>(acc, f); break;
+    case 3: k1_mma_chunk_n<NT, 3>(acc, f); break;
+    case 2: k1_mma_chunk_n<NT, 2>(acc, f); break;
+    case 1: k1_mma_chunk_n<NT, 1>(acc, f); break;
+    default: break;
+  }
+}
+
+// End of a pass: Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over the warp's NACT row-blocks, then
+// clear the Z^T accumulators.
+template <int NT, int NACT>
+__device__ __forceinline__ void k1_second_gemm_n(double (&yacc)[NT][NT][2],
+                                                 double (&acc)[K1_RB][NT][2], uint32_t ub0,
+                                                 uint32_t u_nt_stride) {
+#pragma unroll
+  for (int rb = 0; rb < NACT; ++rb) {
+    const uint32_t ub = ub0 + (uint32_t)(rb * K1_NWARP * 8 * 8);  // 8 rows per block, NWARP apart
+#pragma unroll
+    for (int nk = 0; nk < NT; ++nk) {
+      const double b0 = lds64(ub + nk * u_nt_stride);       // U[row0 + c    ][nk*8+g]
+      const double b1 = lds64(ub + nk * u_nt_stride + 32);  // U[row0 + c + 4][nk*8+g]
+#pragma unroll
+      for (int nl = 0; nl < NT; ++nl) {
+        dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][0], b0);
+        dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][1], b1);
       }
+    }
+  }
+#pragma unroll
+  for (int rb = 0; rb < K1_RB; ++rb)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[rb][nt][0] = acc[rb][nt][1] = 0.0;
+}
+
+template <int NT>
+__device__ __forceinline__ void k1_second_gemm(double (&yacc)[NT][NT][2],
+                                               double (&acc)[K1_RB][NT][2], uint32_t ub0,
+                                               uint32_t u_nt_stride, int nact) {
+  switch (nact) {
+    case 4: k1_second_gemm_n<NT, 4>(yacc, acc, ub0, u_nt_stride); break;
+    case 3: k1_second_gemm_n<NT, 3>(yacc, acc, ub0, u_nt_stride); break;
+    case 2: k1_second_gemm_n<NT, 2>(yacc, acc, ub0, u_nt_stride); break;
+    case 1: k1_second_gemm_n<NT, 1>(yacc, acc, ub0, u_nt_stride); break;
+    default: k1_second_gemm_n<NT, 0>(yacc, acc, ub0, u_nt_stride); break;
+  }
 }
 
 template <int NT>
@@ -190,14 +241,11 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   }
 
   for (long ci = 0; ci < total_chunks; ++ci) {
-    bool act[K1_RB];
-#pragma unroll
-    for (int rb = 0; rb < K1_RB; ++rb) act[rb] = (rb * K1_NWARP + warp) < nrb_pass;
-    const bool full = nrb_pass == K1_NWARP * K1_RB;
+    // this warp's row-blocks rb*NWARP+warp < nrb_pass form a prefix of length nact (0..RB)
+    const int nact = max(0, min(K1_RB, (nrb_pass - warp + K1_NWARP - 1) / K1_NWARP));
 
     load_frag(f1, stage, kc, 1);
-    if (full) k1_mma_chunk<NT, true>(acc, f0, act);
-    else k1_mma_chunk<NT, false>(acc, f0, act);
+    k1_mma_chunk<NT>(acc, f0, nact);
 
     // Prefetch the first half of the next chunk (next stage of the ring).
     int nstage_i = stage + 1;
@@ -219,8 +267,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       load_frag(f0, nstage_i, nkc_i, 0);
     }
 
-    if (full) k1_mma_chunk<NT, true>(acc, f1, act);
-    else k1_mma_chunk<NT, false>(acc, f1, act);
+    k1_mma_chunk<NT>(acc, f1, nact);
 
     // All shared-memory reads of `stage` are complete (their values fed the MMAs above).
     __syncwarp();
@@ -228,25 +275,9 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
 
     if (kc == nkc - 1) {
       // ---- end of pass: Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over this warp's rows ----
-#pragma unroll
-      for (int rb = 0; rb < K1_RB; ++rb) {
-        if (act[rb]) {
-          const int row0 = pass * K1_ROWS + (rb * K1_NWARP + warp) * 8;
-          const uint32_t ub = ut_base + uoff_b + (uint32_t)(row0 * 8);
-#pragma unroll
-          for (int nk = 0; nk < NT; ++nk) {
-            const double b0 = lds64(ub + nk * u_nt_stride);        // U[row0 + c    ][nk*8+g]
-            const double b1 = lds64(ub + nk * u_nt_stride + 32);   // U[row0 + c + 4][nk*8+g]
-#pragma unroll
-            for (int nl = 0; nl < NT; ++nl) {
-              dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][0], b0);
-              dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][1], b1);
-            }
-          }
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[rb][nt][0] = acc[rb][nt][1] = 0.0;
-      }
+      k1_second_gemm<NT>(yacc, acc,
+                         ut_base + uoff_b + (uint32_t)((pass * K1_ROWS + warp * 8) * 8),
+                         u_nt_stride, nact);
       if (pass == npass - 1) {
         // ---- end of slab: fixed-order reduction of the 8 per-warp partials, store Y^T ----
         named_bar_sync(1, K1_NWARP * 32);  // previous slab's readers are done with Ypart

@@ -3,7 +3,7 @@
 // large synthetic problems.  Usage:
 //   oo_probe peaks
 //   oo_probe check  M N [seed]
-//   oo_probe time   M N [mloc] [reps]
+//   oo_probe time   M N [mloc] [reps] [dense]
 //   oo_probe opt    M N
 #include <cuda_runtime.h>
 
@@ -264,7 +264,7 @@ __global__ void fill_hash(double* p, size_t n, unsigned long long seed) {
   }
 }
 
-static int cmd_time(int M, int N, int mloc, int reps) {
+static int cmd_time(int M, int N, int mloc, int reps, bool dense) {
   const size_t M3 = (size_t)M * M * M;
   const size_t gcount = (size_t)mloc * M3;
   printf("# allocating g shard: %.2f GB\n", gcount * 8.0 / 1e9);
@@ -284,6 +284,8 @@ static int cmd_time(int M, int N, int mloc, int reps) {
   CK(oo_create(0, M, N, 0, mloc, &ctx));
   CK(oo_set_integrals(ctx, dh, dg, OO_G_V4_SYMMETRIC));
   CK(oo_set_rdms(ctx, dD, dG));
+  CK(oo_set_pair_symmetry(ctx, dense ? 0 : 1));
+  const int nslab = oo_streamed_slabs(ctx);
   CK(oo_set_timing(ctx, 1));
   float ms[5], best[5] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f}, sum[5] = {0, 0, 0, 0, 0};
   for (int w = 0; w < 3; ++w) {
@@ -298,16 +300,16 @@ static int cmd_time(int M, int N, int mloc, int reps) {
       sum[i] += ms[i];
     }
   }
-  const double bytes = gcount * 8.0;
-  const double fl1 = 2.0 * mloc * M3 * N + 2.0 * mloc * (double)M * M * N * N;  // K1 flops
-  const double flp = 2.0 * mloc * M3 * (8.0 * ((N + 7) / 8)) +
-                     2.0 * mloc * (double)M * M * 64.0 * ((N + 7) / 8) * ((N + 7) / 8);
-  printf("{\"cmd\": \"time\", \"M\": %d, \"N\": %d, \"mloc\": %d, \"reps\": %d, "
+  const double bytes = (double)nslab * M * M * 8.0;
+  const double fl1 = (double)nslab * (2.0 * M * M * N + 2.0 * M * N * N);  // K1 flops
+  const double Npd = 8.0 * ((N + 7) / 8);
+  const double flp = (double)nslab * (2.0 * M * M * Npd + 2.0 * M * Npd * Npd);
+  printf("{\"cmd\": \"time\", \"mode\": \"%s\", \"slabs\": %d, \"M\": %d, \"N\": %d, \"mloc\": %d, \"reps\": %d, "
          "\"k1_ms_avg\": %.4f, \"k1_ms_min\": %.4f, \"qc_ms\": %.4f, \"gc_ms\": %.4f, "
          "\"fin_ms\": %.4f, \"eval_ms_avg\": %.4f, \"eval_ms_min\": %.4f, "
          "\"k1_gbs\": %.1f, \"k1_tflops_alg\": %.2f, \"k1_tflops_padded\": %.2f, "
          "\"evals_per_s\": %.2f}\n",
-         M, N, mloc, reps, sum[0] / reps, best[0], sum[1] / reps, sum[2] / reps, sum[3] / reps,
+         dense ? "dense" : "pair-symmetric", nslab, M, N, mloc, reps, sum[0] / reps, best[0], sum[1] / reps, sum[2] / reps, sum[3] / reps,
          sum[4] / reps, best[4], bytes / (sum[0] / reps * 1e-3) / 1e9,
          fl1 / (sum[0] / reps * 1e-3) / 1e12, flp / (sum[0] / reps * 1e-3) / 1e12,
          1e3 / (sum[4] / reps));
@@ -355,7 +357,8 @@ int main(int argc, char** argv) {
   const int M = atoi(argv[2]), N = atoi(argv[3]);
   if (cmd == "check") return cmd_check(M, N, argc > 4 ? (unsigned)atoi(argv[4]) : 1u);
   if (cmd == "time")
-    return cmd_time(M, N, argc > 4 ? atoi(argv[4]) : M, argc > 5 ? atoi(argv[5]) : 10);
+    return cmd_time(M, N, argc > 4 ? atoi(argv[4]) : M, argc > 5 ? atoi(argv[5]) : 10,
+                    argc > 6 && std::string(argv[6]) == "dense");
   if (cmd == "opt") return cmd_opt(M, N);
   return 64;
 }

@@ -22,6 +22,14 @@ def shard_range(M: int, rank: int, world: int) -> Tuple[int, int]:
     return t0, base + (1 if rank < extra else 0)
 
 
+def pair_selected(t: int, q: int) -> bool:
+    """Which slab of the pair {(t,q),(q,t)} the pair-symmetric mode streams (mirror of
+    oo::pair_selected in csrc/oo_k2.cuh): checkerboard, so every row keeps about M/2 slabs."""
+    if t == q:
+        return True
+    return (t < q) if ((t + q) % 2 == 0) else (t > q)
+
+
 def attach_nccl(engine, group=None) -> None:
     """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed
     (any backend) broadcasts its 128 bytes, every rank joins."""

@@ -132,6 +132,19 @@ class OrbitalEngine:
         _lib.check(self.lib.oo_set_rdms(self._ctx, _ptr(D), _ptr(G)))
         _lib.check(self.lib.oo_synchronize(self._ctx))   # D, G may be freed by the caller now
 
+    def set_pair_symmetry(self, enable: bool) -> None:
+        """Stream one slab of every pair {(t,q),(q,t)} (default) or every slab of the shard."""
+        _lib.check(self.lib.oo_set_pair_symmetry(self._ctx, 1 if enable else 0))
+        self._out.zero_()
+        self._inputs_ready()
+
+    def streamed_slabs(self) -> int:
+        """M x M slabs one evaluation reads from HBM on this GPU."""
+        n = int(self.lib.oo_streamed_slabs(self._ctx))
+        if n < 0:
+            _lib.check(n)
+        return n
+
     # -- multi-GPU -----------------------------------------------------------------------------
     def attach_comm(self, unique_id: bytes, rank: int, world: int) -> None:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

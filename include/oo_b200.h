@@ -82,10 +82,23 @@ int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_hos
  * (weights are folded in by the caller: E is linear in the RDMs). */
 int oo_set_rdms(oo_ctx* ctx, const double* D_dev, const double* G_dev);
 
+/* Pair-symmetric slab mode (default: enabled).  A V4-symmetric tensor satisfies
+ * g[t,q,r,s] = g[q,t,s,r], so the half-transformed tiles obey Y[q,t] = Y[t,q]^T: only one slab of
+ * every pair {(t,q),(q,t)} is streamed from HBM (checkerboard choice: ~M/2 slabs per row, shards
+ * stay balanced) and used for both rows.  With several GPUs every rank then contributes partial
+ * gradient rows for ALL of U, completed by the same all-reduce.  enable=0 streams every slab of the
+ * shard (dense mode: out_dev rows outside the shard are left untouched). */
+int oo_set_pair_symmetry(oo_ctx* ctx, int enable);
+/* Number of M x M slabs one evaluation streams from HBM on this GPU (algorithmic bytes =
+ * 8*M*M*slabs). */
+int oo_streamed_slabs(oo_ctx* ctx);
+
 /* ---- evaluation ---------------------------------------------------------------------------- */
-/* Enqueue one evaluation at U_dev [M][N].  out_dev [M*N+1] receives this shard's rows of dE/dU
- * (other rows are left untouched: zero if the buffer was zeroed once) followed by the shard's
- * partial energy.  With one GPU that is E(U) and dE/dU.  Asynchronous on the context stream.
+/* Enqueue one evaluation at U_dev [M][N].  out_dev [M*N+1] receives this GPU's partial dE/dU
+ * (pair-symmetric mode: partial values for every row; dense mode: the shard's rows, other rows
+ * left untouched, i.e. zero if the buffer was zeroed once) followed by the GPU's partial energy;
+ * the sum over GPUs is E(U), dE/dU.  With one GPU no reduction is needed.  Asynchronous on the
+ * context stream.
  * Replaces base.py:534-582 (compute_rotated_energy) + pupo.py:85-103 (autograd gradient). */
 int oo_energy_grad(oo_ctx* ctx, const double* U_dev, double* out_dev);
 /* Same through host buffers: H2D of U, evaluation, all-reduce when a communicator is attached,
