@@ -308,8 +308,7 @@ def main():
                                                "(oo_measure_peaks); DFMA pipe = %.1f TFLOP/s" % dfma,
                                 "algorithmic_flops_per_launch": alg_flops},
             "kernel_ms": {"k1_half_transform": parts[0] / K, "k_qcontract": parts[1] / K,
-                          "k_gamma_contract": parts[2] / K, "k_ud+k_finalize": parts[3] / K,
-                          "eval_total": parts[4] / K},
+                          "k_tail_row": parts[2] / K, "eval_total": parts[4] / K},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": M * N * 8,
                     "d2h_bytes_per_step": (M * N + 1) * 8,
                     "api": "OrbitalEngine.energy_grad_host -> oo_energy_grad_host (host buffers)"},

@@ -114,7 +114,8 @@ struct oo_ctx {
   // workspaces (device)
   double *Y = nullptr, *T3 = nullptr, *Gp = nullptr, *D = nullptr, *A = nullptr, *UD = nullptr,
          *UDt = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
-         *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr;
+         *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr,
+         *YT = nullptr, *Upad = nullptr;
   int hist_cap = 0;
   unsigned int* counter = nullptr;
   // pair-symmetric slab selection (see oo_k2.cuh)
@@ -179,6 +180,8 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag) {
   K1Params p;
   p.U = U;
   p.Y = c->Y;
+  p.YT = c->pair_sym ? c->YT : nullptr;
+  p.Upad = c->Upad;
   p.done_flag = done_flag;
   p.M = c->M;
   p.N = c->N;
@@ -211,9 +214,9 @@ int launch_k1(oo_ctx* c, const double* U, const int* done_flag) {
 }
 
 template <int NT>
-int launch_qc_t(oo_ctx* c, const double* U, const int* done_flag) {
+int launch_qc_t(oo_ctx* c, const int* done_flag) {
   constexpr int Np = NT * 8;
-  const size_t smem = ((size_t)c->M * Np + (size_t)QC_QGROUPS * Np * QC_ECHUNK) * sizeof(double);
+  const size_t smem = qc_smem_bytes(NT, c->M, c->mloc);
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[c->device & 7]) {
     CU_TRY(cudaFuncSetAttribute(k_qcontract<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -223,29 +226,65 @@ int launch_qc_t(oo_ctx* c, const double* U, const int* done_flag) {
   if (smem > 227 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
   QCParams qp;
   qp.Y = c->Y;
-  qp.U = U;
+  qp.YT = c->YT;
+  qp.Upad = c->Upad;
   qp.T3 = c->T3;
   qp.idxmap = c->pair_sym ? c->idxmap : nullptr;
   qp.done_flag = done_flag;
   qp.M = c->M;
-  qp.N = c->N;
   qp.t0 = c->t0;
   qp.mloc = c->mloc;
   qp.row0 = c->pair_sym ? 0 : c->t0;
   qp.nrows = c->pair_sym ? c->M : c->mloc;
   dim3 grid(qp.nrows, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
-  k_qcontract<NT><<<grid, QC_ECHUNK * QC_QGROUPS, smem, c->stream>>>(qp);
+  k_qcontract<NT><<<grid, QC_ECHUNK * QC_GROUPS, smem, c->stream>>>(qp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
 }
 
-int launch_qc(oo_ctx* c, const double* U, const int* done_flag) {
+template <int NT>
+int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag) {
+  TailParams tp;
+  tp.T3 = c->T3;
+  tp.Gp = c->Gp;
+  tp.h = c->h;
+  tp.U = U;
+  tp.Upad = c->Upad;
+  tp.D = c->D;
+  tp.out = out;
+  tp.rowE = c->rowE;
+  tp.counter = c->counter;
+  tp.done_flag = done_flag;
+  tp.M = c->M;
+  tp.N = c->N;
+  tp.t0 = c->t0;
+  tp.mloc = c->mloc;
+  tp.row0 = c->pair_sym ? 0 : c->t0;
+  tp.nrows = c->pair_sym ? c->M : c->mloc;
+  tp.two_body_grad_factor = 4.0;
+  k_tail_row<NT><<<tp.nrows, TAIL_THREADS, 0, c->stream>>>(tp);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag) {
   switch (c->NT) {
-    case 1: return launch_qc_t<1>(c, U, done_flag);
-    case 2: return launch_qc_t<2>(c, U, done_flag);
-    case 3: return launch_qc_t<3>(c, U, done_flag);
-    case 4: return launch_qc_t<4>(c, U, done_flag);
+    case 1: return launch_tail_t<1>(c, U, out, done_flag);
+    case 2: return launch_tail_t<2>(c, U, out, done_flag);
+    case 3: return launch_tail_t<3>(c, U, out, done_flag);
+    case 4: return launch_tail_t<4>(c, U, out, done_flag);
+  }
+  return fail(OO_ERR_INVALID, "unsupported N");
+}
+
+int launch_qc(oo_ctx* c, const int* done_flag) {
+  switch (c->NT) {
+    case 1: return launch_qc_t<1>(c, done_flag);
+    case 2: return launch_qc_t<2>(c, done_flag);
+    case 3: return launch_qc_t<3>(c, done_flag);
+    case 4: return launch_qc_t<4>(c, done_flag);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -259,42 +298,10 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) 
   if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_k1(c, U, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
-  if ((rc = launch_qc(c, U, done_flag))) return rc;
+  if ((rc = launch_qc(c, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
-  {
-    const int L = c->Np * c->Np * c->Np;
-    dim3 grid(c->pair_sym ? c->M : c->mloc, (c->N + GC_AGROUP - 1) / GC_AGROUP);
-    k_gamma_contract<<<grid, 256, 0, c->stream>>>(c->T3, c->Gp, c->A, c->N, L, done_flag);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
-  }
+  if ((rc = launch_tail(c, U, out, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
-  {
-    k_ud<<<c->M, 32, 0, c->stream>>>(U, c->D, c->UD, c->UDt, c->N, done_flag);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
-    FinalizeParams fp;
-    fp.h = c->h;
-    fp.U = U;
-    fp.UD = c->UD;
-    fp.UDt = c->UDt;
-    fp.A = c->A;
-    fp.out = out;
-    fp.rowE = c->rowE;
-    fp.counter = c->counter;
-    fp.done_flag = done_flag;
-    fp.M = c->M;
-    fp.N = c->N;
-    fp.t0 = c->t0;
-    fp.mloc = c->mloc;
-    fp.row0 = c->pair_sym ? 0 : c->t0;
-    fp.nrows = c->pair_sym ? c->M : c->mloc;
-    fp.two_body_grad_factor = 4.0;
-    k_finalize<<<fp.nrows, 128, 0, c->stream>>>(fp);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
-  }
-  if (tm) CU_TRY(cudaEventRecord(c->ev[4], c->stream));
   return OO_OK;
 }
 
@@ -377,6 +384,8 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(double));
   };
   A(&c->Y, (size_t)mloc * M * Np2);
+  A(&c->YT, (size_t)mloc * (M / 2 + 1) * Np2);
+  A(&c->Upad, (size_t)M * c->Np);
   A(&c->T3, (size_t)M * c->Np * Np2);
   A(&c->Gp, (size_t)N * c->Np * Np2);
   A(&c->D, (size_t)N * N);
@@ -436,7 +445,8 @@ int oo_destroy(oo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
-                    c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp};
+                    c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
+                    c->YT,  c->Upad};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (c->counter) cudaFree(c->counter);
@@ -552,7 +562,7 @@ int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_ro
   int rc;
   if (g_rot_dev) {
     if ((rc = launch_k1(c, U_dev, nullptr))) return rc;
-    if ((rc = launch_qc(c, U_dev, nullptr))) return rc;
+    if ((rc = launch_qc(c, nullptr))) return rc;
     k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np,
                                                    c->pair_sym ? 0 : c->t0,
                                                    c->pair_sym ? c->M : c->mloc);
@@ -761,9 +771,10 @@ int oo_set_timing(oo_ctx* c, int enable) {
 int oo_last_timing(oo_ctx* c, float* ms5_host) {
   if (!c || !ms5_host) return fail(OO_ERR_INVALID, "NULL argument");
   if (!c->timing) return fail(OO_ERR_STATE, "timing is not enabled");
-  CU_TRY(cudaEventSynchronize(c->ev[4]));
-  for (int i = 0; i < 4; ++i) CU_TRY(cudaEventElapsedTime(&ms5_host[i], c->ev[i], c->ev[i + 1]));
-  CU_TRY(cudaEventElapsedTime(&ms5_host[4], c->ev[0], c->ev[4]));
+  CU_TRY(cudaEventSynchronize(c->ev[3]));
+  for (int i = 0; i < 3; ++i) CU_TRY(cudaEventElapsedTime(&ms5_host[i], c->ev[i], c->ev[i + 1]));
+  ms5_host[3] = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms5_host[4], c->ev[0], c->ev[3]));
   return OO_OK;
 }
 

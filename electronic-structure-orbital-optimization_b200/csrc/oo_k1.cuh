@@ -34,6 +34,8 @@ constexpr int K1_THREADS = (K1_NWARP + 1) * 32;    // + 1 producer warp
 struct K1Params {
   const double* U;       // [M][N] row-major partial unitary
   double* Y;             // [nslab][Np][Np], element (l,k) of slab = Y_tq[k][l]
+  double* YT;            // optional [nslab][Np][Np] transposed tiles (pair-symmetric mode) or NULL
+  double* Upad;          // optional [M][Np] zero-padded copy of U written by CTA 0
   const int* done_flag;  // optional: non-zero => kernel is a no-op (optimiser already stopped)
   int M, N;
   const int* slab_coord; // optional: slab i lives at tensor coordinate slab_coord[i] = tl*M + q
@@ -128,7 +130,7 @@ __device__ __forceinline__ void k1_second_gemm(double (&yacc)[NT][NT][2],
 }
 
 template <int NT>
-__global__ void __launch_bounds__(K1_THREADS, 1)
+__global__ void __maxnreg__(224)
 k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   constexpr int Np = NT * 8;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
@@ -157,6 +159,13 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   for (int idx = tid; idx < Np * p.upitch; idx += K1_THREADS) {
     const int l = idx / p.upitch, s = idx - l * p.upitch;
     Ut[idx] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+  }
+  // Side product for the tail kernels: the zero-padded row-major copy Upad[M][Np].
+  if (blockIdx.x == 0 && p.Upad != nullptr) {
+    for (int idx = tid; idx < p.M * Np; idx += K1_THREADS) {
+      const int s = idx / Np, l = idx - s * Np;
+      p.Upad[idx] = (l < p.N) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+    }
   }
   __syncthreads();
 
@@ -292,11 +301,15 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
           }
         named_bar_sync(1, K1_NWARP * 32);
         double* out = p.Y + (size_t)slab * Np * Np;
+        double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
         for (int e = tid; e < Np * Np; e += K1_NWARP * 32) {
           double s = 0.0;
 #pragma unroll
           for (int w = 0; w < K1_NWARP; ++w) s += Ypart[w * Np * Np + e];
           out[e] = s;
+          // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
+          // reads both orientations with unit stride
+          if (outT) outT[(e % Np) * Np + e / Np] = s;
         }
       }
     }

@@ -1,8 +1,7 @@
 // K2 family — the cheap tail of the energy/gradient evaluation (HBM/L2-bound, no tensor cores):
 //   k_qcontract      T3[x][j][e]  = sum_q U[q][j] * Y[x,q][e]                (third index contraction)
-//   k_gamma_contract A[x][a]      = sum_{j,e} T3[x][j][e] * Gp[a][j][e]      (2-RDM contraction)
-//   k_ud             UD = U*D, UDt = U*D^T                                    (1-RDM, tiny)
-//   k_finalize       dE/dU rows, partial energy, fixed-order reductions
+//   k_tail_row       A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]  (2-RDM contraction), the 1-RDM
+//                    terms, dE/dU rows, partial energy; fixed-order reductions, one launch
 //   k_rotate_g       g'[i][j][k][l] = sum_x U[x][i] * T3[x][j][k][l]          (rotated Hamiltonian)
 // Together with K1 they restate, in the spatial-orbital picture and with an analytic gradient,
 //   base_opt_orb_solver.py:554-563 (energy) and
@@ -26,144 +25,124 @@ __host__ __device__ inline bool pair_selected(int t, int q) {
   return (((t + q) & 1) == 0) ? (t < q) : (t > q);
 }
 
-constexpr int QC_ECHUNK = 64;  // e-values per CTA in k_qcontract
-constexpr int QC_QGROUPS = 4;  // term-range split inside the CTA
+constexpr int QC_ECHUNK = 64;   // e-values per CTA in k_qcontract
+constexpr int QC_GROUPS = 8;    // the term list is split 8 ways inside the CTA (512 threads)
+constexpr int QC_TBIT = 1 << 30;  // term flag: read the transposed tile copy
 
 struct QCParams {
   const double* Y;       // [nslab][Np*Np]
-  const double* U;       // [M][N]
+  const double* YT;      // [nslab][Np*Np] transposed tiles (pair-symmetric mode)
+  const double* Upad;    // [M][Np] zero-padded U (written by K1's CTA 0)
   double* T3;            // [nrows][Np][Np*Np]
   const int* idxmap;     // pair-symmetric mode: [mloc][M] slab index or -1; NULL = dense (tl*M+q)
   const int* done_flag;
-  int M, N, t0, mloc;
+  int M, t0, mloc;
   int row0, nrows;       // rows x produced: dense [t0, t0+mloc); pair-symmetric [0, M)
 };
 
-// grid (nrows, ceil(Np^2/64)), block 256, dynamic smem: M*Np doubles (U padded) + 4*Np*64 doubles
+static inline size_t qc_smem_bytes(int NT, int M, int mloc) {
+  const int Np = NT * 8;
+  return (size_t)QC_GROUPS * Np * QC_ECHUNK * sizeof(double) + (size_t)2 * (M + mloc) * sizeof(int);
+}
+
+// grid (nrows, ceil(Np^2/64)), block 512.
+// Row x:  T3[x][j][e] = sum over the tiles that involve row x of  U[partner][j] * tile[e]
+//   own slabs (x,q)   : partner q, tile Y[slab]      (x in this GPU's shard)
+//   mirrored (t,x)    : partner t, tile YT[slab]     (pair-symmetric mode, t in the shard, t != x)
 template <int NT>
-__global__ void __launch_bounds__(QC_ECHUNK* QC_QGROUPS) k_qcontract(const QCParams p) {
+__global__ void __launch_bounds__(QC_ECHUNK* QC_GROUPS) k_qcontract(const QCParams p) {
   constexpr int Np = NT * 8, Np2 = Np * Np;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   extern __shared__ double qc_smem[];
-  double* Us = qc_smem;                          // [M][Np]
-  double* red = qc_smem + (size_t)p.M * Np;      // [QGROUPS][Np][ECHUNK]
-  const int tid = threadIdx.x, M = p.M;
-  for (int idx = tid; idx < M * Np; idx += blockDim.x) {
-    const int q = idx / Np, j = idx - q * Np;
-    Us[idx] = (j < p.N) ? __ldg(p.U + (size_t)q * p.N + j) : 0.0;
+  double* red = qc_smem;                                         // [GROUPS][Np][ECHUNK]
+  int* s_tile = reinterpret_cast<int*>(red + QC_GROUPS * Np * QC_ECHUNK);
+  int* s_urow = s_tile + (p.M + p.mloc);
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31, M = p.M;
+  const int x = p.row0 + blockIdx.x;
+  const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+
+  // ---- compacted term list (one warp, ballot prefix) ----
+  if (tid < 32) {
+    const int nterms = p.idxmap ? M + p.mloc : M;
+    int cnt = 0;
+    for (int base = 0; base < nterms; base += 32) {
+      const int n = base + lane;
+      int tile = -1, urow = 0;
+      if (n < nterms) {
+        if (n < M) {
+          if (mine) {
+            tile = p.idxmap ? __ldg(p.idxmap + (size_t)(x - p.t0) * M + n) : (x - p.t0) * M + n;
+            urow = n;
+          }
+        } else {
+          const int tl = n - M;
+          if (p.t0 + tl != x) {                  // the diagonal slab is already in the first list
+            tile = __ldg(p.idxmap + (size_t)tl * M + x);
+            if (tile >= 0) tile |= QC_TBIT;
+            urow = p.t0 + tl;
+          }
+        }
+      }
+      const bool v = tile >= 0;
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        s_tile[pos] = tile;
+        s_urow[pos] = urow;
+      }
+      cnt += __popc(m);
+    }
+    if (lane == 0) s_count = cnt;
   }
   __syncthreads();
-  const int x = p.row0 + blockIdx.x;
-  const int el = tid & (QC_ECHUNK - 1), qg = tid / QC_ECHUNK;
+
+  const int el = tid & (QC_ECHUNK - 1), grp = tid / QC_ECHUNK;
   const int e = blockIdx.y * QC_ECHUNK + el;
   const bool valid = e < Np2;
   const int ee = valid ? e : 0;
-  const int eT = (ee % Np) * Np + ee / Np;       // transposed position inside a tile
   double acc[Np];
 #pragma unroll
   for (int j = 0; j < Np; ++j) acc[j] = 0.0;
-  const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
-  // term list: n in [0,M): slab (x,q=n) of my own row; n in [M, M+mloc): slab (t=t0+n-M, x)
-  // transposed (pair-symmetric mode only)
-  const int nterms = p.idxmap ? M + p.mloc : M;
-  const int per = (nterms + QC_QGROUPS - 1) / QC_QGROUPS;
-  const int n0 = qg * per, n1 = min(nterms, n0 + per);
-#pragma unroll 2
+  const int cnt = s_count;
+  const int per = (cnt + QC_GROUPS - 1) / QC_GROUPS;
+  const int n0 = grp * per, n1 = min(cnt, n0 + per);
+#pragma unroll 4
   for (int n = n0; n < n1; ++n) {
-    int slab, urow, epos;
-    if (n < M) {
-      if (!mine) continue;
-      slab = p.idxmap ? __ldg(p.idxmap + (size_t)(x - p.t0) * M + n) : (x - p.t0) * M + n;
-      urow = n;
-      epos = ee;
-    } else {
-      const int tl = n - M;
-      if (p.t0 + tl == x) continue;              // the diagonal slab is already in the first list
-      slab = __ldg(p.idxmap + (size_t)tl * M + x);
-      urow = p.t0 + tl;
-      epos = eT;
-    }
-    if (slab < 0) continue;
-    const double y = valid ? __ldg(p.Y + (size_t)slab * Np2 + epos) : 0.0;
-    const double2* u2 = reinterpret_cast<const double2*>(Us + urow * Np);
+    const int tile = s_tile[n];
+    const double* src = (tile & QC_TBIT) ? p.YT : p.Y;
+    const double y = __ldg(src + (size_t)(tile & (QC_TBIT - 1)) * Np2 + ee);
+    const double2* u2 = reinterpret_cast<const double2*>(p.Upad + (size_t)s_urow[n] * Np);
 #pragma unroll
     for (int j = 0; j < Np / 2; ++j) {
-      const double2 u = u2[j];
+      const double2 u = __ldg(u2 + j);
       acc[2 * j] = fma(u.x, y, acc[2 * j]);
       acc[2 * j + 1] = fma(u.y, y, acc[2 * j + 1]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < Np; ++j) red[(qg * Np + j) * QC_ECHUNK + el] = acc[j];
+  for (int j = 0; j < Np; ++j) red[(grp * Np + j) * QC_ECHUNK + el] = acc[j];
   __syncthreads();
-  // fixed-order sum over the groups; thread (qg, el) finishes planes j = qg, qg+4, ...
+  // fixed-order sum over the groups; thread (grp, el) finishes planes j = grp, grp+8, ...
   if (valid) {
-    for (int j = qg; j < Np; j += QC_QGROUPS) {
+    for (int j = grp; j < Np; j += QC_GROUPS) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < QC_QGROUPS; ++w) s += red[(w * Np + j) * QC_ECHUNK + el];
+      for (int w = 0; w < QC_GROUPS; ++w) s += red[(w * Np + j) * QC_ECHUNK + el];
       p.T3[((size_t)blockIdx.x * Np + j) * Np2 + e] = s;
     }
   }
 }
 
-constexpr int GC_AGROUP = 4;  // a-values per CTA in k_gamma_contract
-
-// grid (nrows, ceil(N/4)), block 256.  L = Np^3.  A is [nrows][N].
-__global__ void __launch_bounds__(256)
-k_gamma_contract(const double* __restrict__ T3, const double* __restrict__ Gp,
-                 double* __restrict__ A, int N, int L, const int* done_flag) {
-  if (done_flag != nullptr && *done_flag != 0) return;
-  __shared__ double scratch[32];
-  const int t = blockIdx.x, a0 = blockIdx.y * GC_AGROUP;
-  const double* tp = T3 + (size_t)t * L;
-  double acc[GC_AGROUP] = {0.0, 0.0, 0.0, 0.0};
-  const double* gp[GC_AGROUP];
-#pragma unroll
-  for (int i = 0; i < GC_AGROUP; ++i) gp[i] = Gp + (size_t)min(a0 + i, N - 1) * L;
-  for (int idx = threadIdx.x * 2; idx < L; idx += blockDim.x * 2) {
-    const double2 tv = *reinterpret_cast<const double2*>(tp + idx);
-#pragma unroll
-    for (int i = 0; i < GC_AGROUP; ++i) {
-      const double2 gv = __ldg(reinterpret_cast<const double2*>(gp[i] + idx));
-      acc[i] = fma(tv.x, gv.x, acc[i]);
-      acc[i] = fma(tv.y, gv.y, acc[i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < GC_AGROUP; ++i) {
-    const double s = block_sum(acc[i], scratch);
-    if (threadIdx.x == 0 && a0 + i < N) A[(size_t)t * N + a0 + i] = s;
-  }
-}
-
-//   UDt[q][a] = sum_j U[q][j] * D[a][j]   (= U D^T)
-//   UD [q][a] = sum_j U[q][j] * D[j][a]   (= U D)
-// grid M, block 32 (N <= 32).
-__global__ void k_ud(const double* __restrict__ U, const double* __restrict__ D,
-                     double* __restrict__ UD, double* __restrict__ UDt, int N,
-                     const int* done_flag) {
-  if (done_flag != nullptr && *done_flag != 0) return;
-  const int q = blockIdx.x, a = threadIdx.x;
-  if (a >= N) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int j = 0; j < N; ++j) {
-    const double u = U[(size_t)q * N + j];
-    s0 = fma(u, D[j * N + a], s0);
-    s1 = fma(u, D[a * N + j], s1);
-  }
-  UD[(size_t)q * N + a] = s0;
-  UDt[(size_t)q * N + a] = s1;
-}
-
-struct FinalizeParams {
-  const double* h;    // [M][M]
-  const double* U;    // [M][N]
-  const double* UD;   // [M][N]
-  const double* UDt;  // [M][N]
-  const double* A;    // [nrows][N]
-  double* out;        // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
-  double* rowE;       // [nrows]
+struct TailParams {
+  const double* T3;    // [nrows][Np^3]
+  const double* Gp;    // [N][Np^3]
+  const double* h;     // [M][M]
+  const double* U;     // [M][N]
+  const double* Upad;  // [M][Np]
+  const double* D;     // [N][N]
+  double* out;         // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
+  double* rowE;        // [nrows]
   unsigned int* counter;
   const int* done_flag;
   int M, N, t0, mloc;  // shard: the one-body terms are added for rows in [t0, t0+mloc) only
@@ -171,52 +150,106 @@ struct FinalizeParams {
   double two_body_grad_factor;  // 4 for the one-pass (V4-symmetric) gradient
 };
 
-// grid nrows, block 128.  Row x = row0 + blockIdx.x of
-//   dE/dU = 4 A + [x in shard] (h (U D^T) + h^T (U D)),   E_partial = sum_x U[x,:].(A + [..] h U D^T)[x,:]
-__global__ void __launch_bounds__(128) k_finalize(const FinalizeParams p) {
+constexpr int TAIL_THREADS = 256;
+
+// grid nrows, block 256.  Row x = row0 + blockIdx.x:
+//   A[a]   = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                   (2-RDM contraction)
+//   b1, b2 = (h U D^T)[x], (h^T U D)[x]        only for rows of this GPU's shard    (1-RDM terms)
+//   out[x] = 4 A + b1 + b2,   rowE[x] = U[x].(A + b1);  the last CTA adds rowE in fixed order.
+template <int NT>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
+  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ double r1[128], r2[128];
+  __shared__ double s_part[NW][Np];
+  __shared__ double s_A[Np], s_b1[Np], s_b2[Np], s_hu[Np], s_htu[Np];
+  __shared__ double s_r1[TAIL_THREADS], s_r2[TAIL_THREADS];
+  __shared__ double scratch[32];
   __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int xl = blockIdx.x, x = p.row0 + xl, N = p.N, M = p.M;
   const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
-  const int nparts = 128 / N > 0 ? 128 / N : 1;  // N <= 32 -> at least 4 parts
-  const int a = threadIdx.x % N, part = threadIdx.x / N;
-  double s1 = 0.0, s2 = 0.0;
+
+  // ---- phase 1: A[a] ----
+  double acc[Np];
+#pragma unroll
+  for (int a = 0; a < Np; ++a) acc[a] = 0.0;
+  const double* tp = p.T3 + (size_t)xl * L;
+  for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
+    const double2 tv = *reinterpret_cast<const double2*>(tp + idx);
+#pragma unroll
+    for (int a = 0; a < Np; ++a) {
+      if (a < N) {
+        const double2 gv = __ldg(reinterpret_cast<const double2*>(p.Gp + (size_t)a * L + idx));
+        acc[a] = fma(tv.x, gv.x, acc[a]);
+        acc[a] = fma(tv.y, gv.y, acc[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < Np; ++a) {
+    double v = acc[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][a] = v;
+  }
+  // ---- phase 2: one-body row terms (this GPU's rows only) ----
+  const int j = tid % Np, part = tid / Np, nparts = TAIL_THREADS / Np;
+  double r1 = 0.0, r2 = 0.0;
   if (mine && part < nparts) {
     for (int q = part; q < M; q += nparts) {
-      s1 = fma(p.h[(size_t)x * M + q], p.UDt[(size_t)q * N + a], s1);
-      s2 = fma(p.h[(size_t)q * M + x], p.UD[(size_t)q * N + a], s2);
+      const double u = __ldg(p.Upad + (size_t)q * Np + j);
+      r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
+      r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
     }
   }
-  r1[threadIdx.x] = s1;
-  r2[threadIdx.x] = s2;
+  s_r1[tid] = r1;
+  s_r2[tid] = r2;
   __syncthreads();
-  if (threadIdx.x < N) {
-    double b1 = 0.0, b2 = 0.0;
+  if (tid < Np) {
+    double a_sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a_sum += s_part[w][tid];
+    s_A[tid] = a_sum;
+    double hu = 0.0, htu = 0.0;
     for (int w = 0; w < nparts; ++w) {
-      b1 += r1[w * N + threadIdx.x];
-      b2 += r2[w * N + threadIdx.x];
+      hu += s_r1[w * Np + tid];
+      htu += s_r2[w * Np + tid];
     }
-    const double av = p.A[(size_t)xl * N + threadIdx.x];
-    p.out[(size_t)x * N + threadIdx.x] = p.two_body_grad_factor * av + b1 + b2;
-    r1[threadIdx.x] = p.U[(size_t)x * N + threadIdx.x] * (av + b1);
+    s_hu[tid] = hu;
+    s_htu[tid] = htu;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid < N) {
+    double b1 = 0.0, b2 = 0.0;
+    if (mine) {
+      for (int jj = 0; jj < N; ++jj) {
+        b1 = fma(s_hu[jj], __ldg(p.D + tid * N + jj), b1);    // (hU) D^T
+        b2 = fma(s_htu[jj], __ldg(p.D + jj * N + tid), b2);   // (h^T U) D
+      }
+    }
+    const double av = s_A[tid];
+    p.out[(size_t)x * N + tid] = p.two_body_grad_factor * av + b1 + b2;
+    s_b1[tid] = __ldg(p.U + (size_t)x * N + tid) * (av + b1);
+  }
+  __syncthreads();
+  if (tid == 0) {
     double e = 0.0;
-    for (int i = 0; i < N; ++i) e += r1[i];
+    for (int i = 0; i < N; ++i) e += s_b1[i];
     p.rowE[xl] = e;
     __threadfence();
     const unsigned int prev = atomicAdd(p.counter, 1u);
     is_last = (prev == (unsigned int)(gridDim.x - 1));
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {
     __threadfence();
-    double e = 0.0;
-    for (int i = 0; i < p.nrows; ++i) e += ((volatile double*)p.rowE)[i];
-    p.out[(size_t)M * N] = e;
-    *p.counter = 0u;
+    double v = 0.0;
+    for (int i = tid; i < p.nrows; i += TAIL_THREADS) v += ((volatile double*)p.rowE)[i];
+    v = block_sum(v, scratch);                  // fixed tree: deterministic
+    if (tid == 0) {
+      p.out[(size_t)M * N] = v;
+      *p.counter = 0u;
+    }
   }
 }
 

@@ -135,8 +135,9 @@ int oo_allreduce(oo_ctx* ctx, double* buf_dev, size_t count);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Average device time (ms) of the kernels of the last oo_energy_grad call, measured with CUDA
- * events on the context stream: [0] K1 half-transform, [1] q-contraction, [2] gamma contraction,
- * [3] one-body + finalize, [4] whole evaluation.  Requires oo_set_timing(ctx,1) beforehand. */
+ * events on the context stream: [0] K1 half-transform, [1] q-contraction, [2] row tail (2-RDM
+ * contraction + one-body terms + energy), [3] reserved (0), [4] whole evaluation.  Requires
+ * oo_set_timing(ctx,1) beforehand. */
 int oo_set_timing(oo_ctx* ctx, int enable);
 int oo_last_timing(oo_ctx* ctx, float* ms5_host);
 /* Number of kernels launched by this context since creation. */
