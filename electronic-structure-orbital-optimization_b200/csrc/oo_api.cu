@@ -217,13 +217,13 @@ template <int NT>
 int launch_qc_t(oo_ctx* c, const int* done_flag) {
   constexpr int Np = NT * 8;
   const size_t smem = qc_smem_bytes(NT, c->M, c->mloc);
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  if (!attr_set[c->device & 7]) {
+  if (smem > 200 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
+  static size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (smem > 48 * 1024 && attr_smem[c->device & 7] < smem) {
     CU_TRY(cudaFuncSetAttribute(k_qcontract<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                227 * 1024));
-    attr_set[c->device & 7] = true;
+                                (int)smem));
+    attr_smem[c->device & 7] = smem;
   }
-  if (smem > 227 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
   QCParams qp;
   qp.Y = c->Y;
   qp.YT = c->YT;

@@ -129,8 +129,10 @@ __device__ __forceinline__ void k1_second_gemm(double (&yacc)[NT][NT][2],
   }
 }
 
+// 9 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
+// 65536 / 384 = 168 per thread; NT <= 2 needs ~142, NT = 3 fits, NT = 4 spills a little.
 template <int NT>
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(K1_THREADS, 1)
 k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   constexpr int Np = NT * 8;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
