@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
   constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   __shared__ double s_part[NW][Np];
-  __shared__ double s_A[Np], s_b1[Np], s_b2[Np], s_hu[Np], s_htu[Np];
+  __shared__ double s_A[Np], s_b1[Np], s_hu[Np], s_htu[Np];
   __shared__ double s_r1[TAIL_THREADS], s_r2[TAIL_THREADS];
   __shared__ double scratch[32];
   __shared__ bool is_last;
