@@ -115,7 +115,9 @@ struct oo_ctx {
   double *Y = nullptr, *T3 = nullptr, *Gp = nullptr, *D = nullptr, *A = nullptr, *UD = nullptr,
          *UDt = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
          *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr,
-         *YT = nullptr, *Upad = nullptr;
+         *YT = nullptr, *Upad = nullptr, *B1 = nullptr, *B12 = nullptr;
+  cudaStream_t aux = nullptr;       // one-body terms run here, concurrently with K1
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int hist_cap = 0;
   unsigned int* counter = nullptr;
   // pair-symmetric slab selection (see oo_k2.cuh)
@@ -222,6 +224,8 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
   if (smem > 48 * 1024 && attr_smem[c->device & 7] < smem) {
     CU_TRY(cudaFuncSetAttribute(k_qcontract<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_qcontract<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
     attr_smem[c->device & 7] = smem;
   }
   QCParams qp;
@@ -237,7 +241,7 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
   qp.row0 = c->pair_sym ? 0 : c->t0;
   qp.nrows = c->pair_sym ? c->M : c->mloc;
   dim3 grid(qp.nrows, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
-  k_qcontract<NT><<<grid, QC_ECHUNK * QC_GROUPS, smem, c->stream>>>(qp);
+  k_qcontract<NT><<<grid, QC_THREADS, smem, c->stream>>>(qp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
@@ -248,10 +252,9 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag)
   TailParams tp;
   tp.T3 = c->T3;
   tp.Gp = c->Gp;
-  tp.h = c->h;
   tp.U = U;
-  tp.Upad = c->Upad;
-  tp.D = c->D;
+  tp.B1 = c->B1;
+  tp.B12 = c->B12;
   tp.out = out;
   tp.rowE = c->rowE;
   tp.counter = c->counter;
@@ -263,7 +266,8 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag)
   tp.row0 = c->pair_sym ? 0 : c->t0;
   tp.nrows = c->pair_sym ? c->M : c->mloc;
   tp.two_body_grad_factor = 4.0;
-  k_tail_row<NT><<<tp.nrows, TAIL_THREADS, 0, c->stream>>>(tp);
+  constexpr int R = tail_rows(NT);
+  k_tail_row<NT><<<(tp.nrows + R - 1) / R, TAIL_THREADS, 0, c->stream>>>(tp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
@@ -295,11 +299,31 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) 
   if (!c->have_rdms) return fail(OO_ERR_STATE, "oo_set_rdms has not been called");
   const bool tm = c->timing;
   int rc;
+  // fork: the one-body rows do not depend on K1 and run on the aux stream next to it
+  CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+  {
+    OneBodyParams ob;
+    ob.h = c->h;
+    ob.U = U;
+    ob.D = c->D;
+    ob.B1 = c->B1;
+    ob.B12 = c->B12;
+    ob.done_flag = done_flag;
+    ob.M = c->M;
+    ob.N = c->N;
+    ob.t0 = c->t0;
+    k_onebody<<<c->mloc, 256, 0, c->aux>>>(ob);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  CU_TRY(cudaEventRecord(c->ev_join, c->aux));
   if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_k1(c, U, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
   if ((rc = launch_qc(c, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));   // join
   if ((rc = launch_tail(c, U, out, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
   return OO_OK;
@@ -386,6 +410,8 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->Y, (size_t)mloc * M * Np2);
   A(&c->YT, (size_t)mloc * (M / 2 + 1) * Np2);
   A(&c->Upad, (size_t)M * c->Np);
+  A(&c->B1, (size_t)mloc * N);
+  A(&c->B12, (size_t)mloc * N);
   A(&c->T3, (size_t)M * c->Np * Np2);
   A(&c->Gp, (size_t)N * c->Np * Np2);
   A(&c->D, (size_t)N * N);
@@ -426,6 +452,9 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   // A blocking stream: it orders itself against the legacy default stream, which is where a host
   // framework (torch) produces the input tensors unless told otherwise.
   if (e == cudaSuccess) e = cudaStreamCreate(&c->stream);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
     e = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming);
@@ -446,7 +475,7 @@ int oo_destroy(oo_ctx* c) {
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
-                    c->YT,  c->Upad};
+                    c->YT,  c->Upad, c->B1,    c->B12};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (c->counter) cudaFree(c->counter);
@@ -459,6 +488,12 @@ int oo_destroy(oo_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->poll_ev)
     if (ev) cudaEventDestroy(ev);
+  if (c->aux) {
+    cudaStreamSynchronize(c->aux);
+    cudaStreamDestroy(c->aux);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return OO_OK;

@@ -1,7 +1,8 @@
 // K2 family — the cheap tail of the energy/gradient evaluation (HBM/L2-bound, no tensor cores):
 //   k_qcontract      T3[x][j][e]  = sum_q U[q][j] * Y[x,q][e]                (third index contraction)
-//   k_tail_row       A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]  (2-RDM contraction), the 1-RDM
-//                    terms, dE/dU rows, partial energy; fixed-order reductions, one launch
+//   k_onebody        (h U D^T)[x], (h^T U D)[x] for the shard's rows   (1-RDM terms; aux stream)
+//   k_tail_row       A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]  (2-RDM contraction), dE/dU
+//                    rows, partial energy; fixed-order reductions, one launch
 //   k_rotate_g       g'[i][j][k][l] = sum_x U[x][i] * T3[x][j][k][l]          (rotated Hamiltonian)
 // Together with K1 they restate, in the spatial-orbital picture and with an analytic gradient,
 //   base_opt_orb_solver.py:554-563 (energy) and
@@ -25,9 +26,12 @@ __host__ __device__ inline bool pair_selected(int t, int q) {
   return (((t + q) & 1) == 0) ? (t < q) : (t > q);
 }
 
-constexpr int QC_ECHUNK = 64;   // e-values per CTA in k_qcontract
-constexpr int QC_GROUPS = 8;    // the term list is split 8 ways inside the CTA (512 threads)
-constexpr int QC_TBIT = 1 << 30;  // term flag: read the transposed tile copy
+constexpr int QC_ECHUNK = 64;    // e-values per CTA in k_qcontract (each lane owns 2)
+constexpr int QC_LANES = QC_ECHUNK / 2;
+constexpr int QC_GROUPS = 8;     // the term list is split 8 ways inside the CTA
+constexpr int QC_THREADS = QC_LANES * QC_GROUPS;   // 256
+constexpr int QC_UNROLL = 8;     // tile loads in flight per thread
+constexpr int QC_TBIT = 1 << 30; // term flag: read the transposed tile copy
 
 struct QCParams {
   const double* Y;       // [nslab][Np*Np]
@@ -45,12 +49,13 @@ static inline size_t qc_smem_bytes(int NT, int M, int mloc) {
   return (size_t)QC_GROUPS * Np * QC_ECHUNK * sizeof(double) + (size_t)2 * (M + mloc) * sizeof(int);
 }
 
-// grid (nrows, ceil(Np^2/64)), block 512.
+// grid (nrows, ceil(Np^2/64)), block 256.
 // Row x:  T3[x][j][e] = sum over the tiles that involve row x of  U[partner][j] * tile[e]
 //   own slabs (x,q)   : partner q, tile Y[slab]      (x in this GPU's shard)
 //   mirrored (t,x)    : partner t, tile YT[slab]     (pair-symmetric mode, t in the shard, t != x)
+// HBM/L2-bound (every tile is read once per orientation): 16-byte loads, 8 in flight per thread.
 template <int NT>
-__global__ void __launch_bounds__(QC_ECHUNK* QC_GROUPS) k_qcontract(const QCParams p) {
+__global__ void __launch_bounds__(QC_THREADS) k_qcontract(const QCParams p) {
   constexpr int Np = NT * 8, Np2 = Np * Np;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   extern __shared__ double qc_smem[];
@@ -97,50 +102,125 @@ __global__ void __launch_bounds__(QC_ECHUNK* QC_GROUPS) k_qcontract(const QCPara
   }
   __syncthreads();
 
-  const int el = tid & (QC_ECHUNK - 1), grp = tid / QC_ECHUNK;
-  const int e = blockIdx.y * QC_ECHUNK + el;
+  const int el = (tid & (QC_LANES - 1)) * 2, grp = tid / QC_LANES;
+  const int e = blockIdx.y * QC_ECHUNK + el;       // this thread owns e and e+1 (Np2 is even)
   const bool valid = e < Np2;
   const int ee = valid ? e : 0;
-  double acc[Np];
+  double acc[Np][2];
 #pragma unroll
-  for (int j = 0; j < Np; ++j) acc[j] = 0.0;
+  for (int j = 0; j < Np; ++j) acc[j][0] = acc[j][1] = 0.0;
   const int cnt = s_count;
   const int per = (cnt + QC_GROUPS - 1) / QC_GROUPS;
   const int n0 = grp * per, n1 = min(cnt, n0 + per);
-#pragma unroll 4
-  for (int n = n0; n < n1; ++n) {
-    const int tile = s_tile[n];
+
+  auto tile_ptr = [&](int tile) {
     const double* src = (tile & QC_TBIT) ? p.YT : p.Y;
-    const double y = __ldg(src + (size_t)(tile & (QC_TBIT - 1)) * Np2 + ee);
-    const double2* u2 = reinterpret_cast<const double2*>(p.Upad + (size_t)s_urow[n] * Np);
+    return reinterpret_cast<const double2*>(src + (size_t)(tile & (QC_TBIT - 1)) * Np2 + ee);
+  };
+  auto accumulate = [&](const double2 y, int urow) {
+    const double2* u2 = reinterpret_cast<const double2*>(p.Upad + (size_t)urow * Np);
 #pragma unroll
     for (int j = 0; j < Np / 2; ++j) {
       const double2 u = __ldg(u2 + j);
-      acc[2 * j] = fma(u.x, y, acc[2 * j]);
-      acc[2 * j + 1] = fma(u.y, y, acc[2 * j + 1]);
+      acc[2 * j][0] = fma(u.x, y.x, acc[2 * j][0]);
+      acc[2 * j][1] = fma(u.x, y.y, acc[2 * j][1]);
+      acc[2 * j + 1][0] = fma(u.y, y.x, acc[2 * j + 1][0]);
+      acc[2 * j + 1][1] = fma(u.y, y.y, acc[2 * j + 1][1]);
     }
-  }
+  };
+  int n = n0;
+#pragma unroll 1
+  for (; n + QC_UNROLL <= n1; n += QC_UNROLL) {
+    double2 y[QC_UNROLL];
+    int ur[QC_UNROLL];
 #pragma unroll
-  for (int j = 0; j < Np; ++j) red[(grp * Np + j) * QC_ECHUNK + el] = acc[j];
+    for (int u = 0; u < QC_UNROLL; ++u) {
+      y[u] = __ldg(tile_ptr(s_tile[n + u]));
+      ur[u] = s_urow[n + u];
+    }
+#pragma unroll
+    for (int u = 0; u < QC_UNROLL; ++u) accumulate(y[u], ur[u]);
+  }
+  for (; n < n1; ++n) accumulate(__ldg(tile_ptr(s_tile[n])), s_urow[n]);
+
+#pragma unroll
+  for (int j = 0; j < Np; ++j)
+    *reinterpret_cast<double2*>(red + (grp * Np + j) * QC_ECHUNK + el) =
+        make_double2(acc[j][0], acc[j][1]);
   __syncthreads();
-  // fixed-order sum over the groups; thread (grp, el) finishes planes j = grp, grp+8, ...
+  // fixed-order sum over the groups; thread (grp, lane) finishes planes j = grp, grp+8, ...
   if (valid) {
     for (int j = grp; j < Np; j += QC_GROUPS) {
-      double s = 0.0;
+      double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-      for (int w = 0; w < QC_GROUPS; ++w) s += red[(w * Np + j) * QC_ECHUNK + el];
-      p.T3[((size_t)blockIdx.x * Np + j) * Np2 + e] = s;
+      for (int w = 0; w < QC_GROUPS; ++w) {
+        const double2 v = *reinterpret_cast<const double2*>(red + (w * Np + j) * QC_ECHUNK + el);
+        s.x += v.x;
+        s.y += v.y;
+      }
+      *reinterpret_cast<double2*>(p.T3 + ((size_t)blockIdx.x * Np + j) * Np2 + e) = s;
     }
+  }
+}
+
+// One-body gradient rows of this GPU's shard (independent of K1: runs on the aux stream).
+//   B1[xl][a]  = (h U D^T)[x][a]            B12[xl][a] = (h U D^T + h^T U D)[x][a],  x = t0 + xl
+// grid mloc, block 256.
+struct OneBodyParams {
+  const double* h;   // [M][M]
+  const double* U;   // [M][N]
+  const double* D;   // [N][N]
+  double* B1;        // [mloc][N]
+  double* B12;       // [mloc][N]
+  const int* done_flag;
+  int M, N, t0;
+};
+
+__global__ void __launch_bounds__(256) k_onebody(const OneBodyParams p) {
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  __shared__ double s_r1[256], s_r2[256], s_hu[32], s_htu[32];
+  const int tid = threadIdx.x, N = p.N, M = p.M;
+  const int x = p.t0 + blockIdx.x;
+  const int j = tid % N, part = tid / N, nparts = 256 / N;
+  double r1 = 0.0, r2 = 0.0;
+  if (part < nparts) {
+#pragma unroll 4
+    for (int q = part; q < M; q += nparts) {
+      const double u = __ldg(p.U + (size_t)q * N + j);
+      r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
+      r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
+    }
+  }
+  s_r1[tid] = r1;
+  s_r2[tid] = r2;
+  __syncthreads();
+  if (tid < N) {
+    double hu = 0.0, htu = 0.0;
+    for (int w = 0; w < nparts; ++w) {
+      hu += s_r1[w * N + tid];
+      htu += s_r2[w * N + tid];
+    }
+    s_hu[tid] = hu;
+    s_htu[tid] = htu;
+  }
+  __syncthreads();
+  if (tid < N) {
+    double b1 = 0.0, b2 = 0.0;
+    for (int jj = 0; jj < N; ++jj) {
+      b1 = fma(s_hu[jj], __ldg(p.D + tid * N + jj), b1);    // (hU) D^T
+      b2 = fma(s_htu[jj], __ldg(p.D + jj * N + tid), b2);   // (h^T U) D
+    }
+    p.B1[(size_t)blockIdx.x * N + tid] = b1;
+    p.B12[(size_t)blockIdx.x * N + tid] = b1 + b2;
   }
 }
 
 struct TailParams {
   const double* T3;    // [nrows][Np^3]
   const double* Gp;    // [N][Np^3]
-  const double* h;     // [M][M]
   const double* U;     // [M][N]
-  const double* Upad;  // [M][Np]
-  const double* D;     // [N][N]
+  const double* B1;    // [mloc][N]  one-body rows of the shard
+  const double* B12;   // [mloc][N]
   double* out;         // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
   double* rowE;        // [nrows]
   unsigned int* counter;
@@ -151,91 +231,87 @@ struct TailParams {
 };
 
 constexpr int TAIL_THREADS = 256;
+// rows per CTA: the 2-RDM is read once per CTA, so more rows = less L2 traffic; bounded by registers
+__host__ __device__ constexpr int tail_rows(int NT) { return NT <= 2 ? 4 : (NT == 3 ? 2 : 1); }
 
-// grid nrows, block 256.  Row x = row0 + blockIdx.x:
-//   A[a]   = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                   (2-RDM contraction)
-//   b1, b2 = (h U D^T)[x], (h^T U D)[x]        only for rows of this GPU's shard    (1-RDM terms)
-//   out[x] = 4 A + b1 + b2,   rowE[x] = U[x].(A + b1);  the last CTA adds rowE in fixed order.
+// grid ceil(nrows / R), block 256.  For the R rows x of the CTA:
+//   A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                 (2-RDM contraction)
+//   out[x]  = 4 A[x] + B12[x] (own rows),   rowE[x] = U[x].(A[x] + B1[x])
+// and the last CTA adds rowE in fixed order into out[M*N].
 template <int NT>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
-  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32;
+  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32, R = tail_rows(NT);
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ double s_part[NW][Np];
-  __shared__ double s_A[Np], s_b1[Np], s_hu[Np], s_htu[Np];
-  __shared__ double s_r1[TAIL_THREADS], s_r2[TAIL_THREADS];
+  __shared__ double s_part[NW][R][Np];
+  __shared__ double s_e[R][Np];
   __shared__ double scratch[32];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int xl = blockIdx.x, x = p.row0 + xl, N = p.N, M = p.M;
-  const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+  const int xl0 = blockIdx.x * R, N = p.N;
 
-  // ---- phase 1: A[a] ----
-  double acc[Np];
+  double acc[R][Np];
 #pragma unroll
-  for (int a = 0; a < Np; ++a) acc[a] = 0.0;
-  const double* tp = p.T3 + (size_t)xl * L;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int a = 0; a < Np; ++a) acc[r][a] = 0.0;
+  const double* tp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) tp[r] = p.T3 + (size_t)min(xl0 + r, p.nrows - 1) * L;
+#pragma unroll 2
   for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
-    const double2 tv = *reinterpret_cast<const double2*>(tp + idx);
+    double2 tv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) tv[r] = *reinterpret_cast<const double2*>(tp[r] + idx);
 #pragma unroll
     for (int a = 0; a < Np; ++a) {
       if (a < N) {
         const double2 gv = __ldg(reinterpret_cast<const double2*>(p.Gp + (size_t)a * L + idx));
-        acc[a] = fma(tv.x, gv.x, acc[a]);
-        acc[a] = fma(tv.y, gv.y, acc[a]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][a] = fma(tv[r].x, gv.x, acc[r][a]);
+          acc[r][a] = fma(tv[r].y, gv.y, acc[r][a]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int a = 0; a < Np; ++a) {
-    double v = acc[a];
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_part[warp][a] = v;
-  }
-  // ---- phase 2: one-body row terms (this GPU's rows only) ----
-  const int j = tid % Np, part = tid / Np, nparts = TAIL_THREADS / Np;
-  double r1 = 0.0, r2 = 0.0;
-  if (mine && part < nparts) {
-    for (int q = part; q < M; q += nparts) {
-      const double u = __ldg(p.Upad + (size_t)q * Np + j);
-      r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
-      r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
-    }
-  }
-  s_r1[tid] = r1;
-  s_r2[tid] = r2;
-  __syncthreads();
-  if (tid < Np) {
-    double a_sum = 0.0;
+    for (int a = 0; a < Np; ++a) {
+      double v = acc[r][a];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) a_sum += s_part[w][tid];
-    s_A[tid] = a_sum;
-    double hu = 0.0, htu = 0.0;
-    for (int w = 0; w < nparts; ++w) {
-      hu += s_r1[w * Np + tid];
-      htu += s_r2[w * Np + tid];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_part[warp][r][a] = v;
     }
-    s_hu[tid] = hu;
-    s_htu[tid] = htu;
-  }
   __syncthreads();
-  if (tid < N) {
-    double b1 = 0.0, b2 = 0.0;
-    if (mine) {
-      for (int jj = 0; jj < N; ++jj) {
-        b1 = fma(s_hu[jj], __ldg(p.D + tid * N + jj), b1);    // (hU) D^T
-        b2 = fma(s_htu[jj], __ldg(p.D + jj * N + tid), b2);   // (h^T U) D
+  if (tid < R * Np) {
+    const int r = tid / Np, a = tid - r * Np;
+    const int xl = xl0 + r, x = p.row0 + xl;
+    double ev = 0.0;
+    if (xl < p.nrows && a < N) {
+      double av = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) av += s_part[w][r][a];
+      const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+      double b1 = 0.0, b12 = 0.0;
+      if (mine) {
+        b1 = p.B1[(size_t)(x - p.t0) * N + a];
+        b12 = p.B12[(size_t)(x - p.t0) * N + a];
       }
+      p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
+      ev = __ldg(p.U + (size_t)x * N + a) * (av + b1);
     }
-    const double av = s_A[tid];
-    p.out[(size_t)x * N + tid] = p.two_body_grad_factor * av + b1 + b2;
-    s_b1[tid] = __ldg(p.U + (size_t)x * N + tid) * (av + b1);
+    s_e[r][a] = ev;
   }
   __syncthreads();
   if (tid == 0) {
-    double e = 0.0;
-    for (int i = 0; i < N; ++i) e += s_b1[i];
-    p.rowE[xl] = e;
+    for (int r = 0; r < R; ++r) {
+      if (xl0 + r < p.nrows) {
+        double e = 0.0;
+        for (int a = 0; a < N; ++a) e += s_e[r][a];
+        p.rowE[xl0 + r] = e;
+      }
+    }
     __threadfence();
     const unsigned int prev = atomicAdd(p.counter, 1u);
     is_last = (prev == (unsigned int)(gridDim.x - 1));
@@ -247,7 +323,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
     for (int i = tid; i < p.nrows; i += TAIL_THREADS) v += ((volatile double*)p.rowE)[i];
     v = block_sum(v, scratch);                  // fixed tree: deterministic
     if (tid == 0) {
-      p.out[(size_t)M * N] = v;
+      p.out[(size_t)p.M * N] = v;
       *p.counter = 0u;
     }
   }
