@@ -122,7 +122,7 @@ struct oo_ctx {
   unsigned int* counter = nullptr;
   // pair-symmetric slab selection (see oo_k2.cuh)
   int* slab_coord = nullptr;    // [nsel] tensor coordinate tl*M+q of the i-th streamed slab
-  int* idxmap = nullptr;        // [mloc][M] slab index or -1
+  int* rowstart = nullptr;      // [mloc] index of the first streamed slab of each row
   int nsel = 0;
   bool pair_sym = true;
   OptState* state = nullptr;
@@ -233,7 +233,7 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
   qp.YT = c->YT;
   qp.Upad = c->Upad;
   qp.T3 = c->T3;
-  qp.idxmap = c->pair_sym ? c->idxmap : nullptr;
+  qp.rowstart = c->pair_sym ? c->rowstart : nullptr;
   qp.done_flag = done_flag;
   qp.M = c->M;
   qp.t0 = c->t0;
@@ -426,22 +426,22 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->Vtmp, MN);
   A(&c->alpha_tmp, 4);
   {
-    // slab tables of the pair-symmetric mode
-    std::vector<int> coord, idx((size_t)mloc * M, -1);
+    // slab tables of the pair-symmetric mode (closed forms: pair_row_count / pair_ith_q)
+    std::vector<int> coord, rowstart(mloc, 0);
     coord.reserve((size_t)mloc * (M / 2 + 1));
-    for (int tl = 0; tl < mloc; ++tl)
-      for (int q = 0; q < M; ++q)
-        if (pair_selected(t0 + tl, q)) {
-          idx[(size_t)tl * M + q] = (int)coord.size();
-          coord.push_back(tl * M + q);
-        }
+    for (int tl = 0; tl < mloc; ++tl) {
+      rowstart[tl] = (int)coord.size();
+      const int t = t0 + tl, cnt = pair_row_count(t, M);
+      for (int i = 0; i < cnt; ++i) coord.push_back(tl * M + pair_ith_q(t, i));
+    }
     c->nsel = (int)coord.size();
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->slab_coord, coord.size() * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->idxmap, idx.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->rowstart, rowstart.size() * sizeof(int));
     if (e == cudaSuccess)
       e = cudaMemcpy(c->slab_coord, coord.data(), coord.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-      e = cudaMemcpy(c->idxmap, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice);
+      e = cudaMemcpy(c->rowstart, rowstart.data(), rowstart.size() * sizeof(int),
+                     cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMalloc((void**)&c->counter, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(c->counter, 0, sizeof(unsigned int));
@@ -480,7 +480,7 @@ int oo_destroy(oo_ctx* c) {
     if (b) cudaFree(b);
   if (c->counter) cudaFree(c->counter);
   if (c->slab_coord) cudaFree(c->slab_coord);
-  if (c->idxmap) cudaFree(c->idxmap);
+  if (c->rowstart) cudaFree(c->rowstart);
   if (c->state) cudaFree(c->state);
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_state) cudaFreeHost(c->pin_state);

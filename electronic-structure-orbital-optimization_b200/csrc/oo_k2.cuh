@@ -26,6 +26,24 @@ __host__ __device__ inline bool pair_selected(int t, int q) {
   return (((t + q) & 1) == 0) ? (t < q) : (t > q);
 }
 
+// Closed forms for the pair-symmetric slab list of one row t (slabs ordered by increasing q):
+//   q < t selected iff q has parity (t+1)&1;  q == t;  q > t selected iff q has parity t&1.
+__host__ __device__ inline int pair_count_below(int t) { return (t + 1) >> 1; }   // selected q < t
+__host__ __device__ inline int pair_row_count(int t, int M) {
+  return pair_count_below(t) + 1 + ((M - 1 - t) >> 1);
+}
+// i-th selected q of row t
+__host__ __device__ inline int pair_ith_q(int t, int i) {
+  const int nb = pair_count_below(t);
+  if (i < nb) return ((t + 1) & 1) + 2 * i;
+  return t + 2 * (i - nb);
+}
+// position of the selected slab (t,q) inside row t's list
+__host__ __device__ inline int pair_rank(int t, int q) {
+  if (q < t) return q >> 1;              // (q + 1 - p) >> 1 with p = parity of q
+  return pair_count_below(t) + ((q - t) >> 1);
+}
+
 constexpr int QC_ECHUNK = 64;    // e-values per CTA in k_qcontract (each lane owns 2)
 constexpr int QC_LANES = QC_ECHUNK / 2;
 constexpr int QC_GROUPS = 8;     // the term list is split 8 ways inside the CTA
@@ -38,7 +56,7 @@ struct QCParams {
   const double* YT;      // [nslab][Np*Np] transposed tiles (pair-symmetric mode)
   const double* Upad;    // [M][Np] zero-padded U (written by K1's CTA 0)
   double* T3;            // [nrows][Np][Np*Np]
-  const int* idxmap;     // pair-symmetric mode: [mloc][M] slab index or -1; NULL = dense (tl*M+q)
+  const int* rowstart;   // pair-symmetric mode: [mloc] first slab index of each row; NULL = dense
   const int* done_flag;
   int M, t0, mloc;
   int row0, nrows;       // rows x produced: dense [t0, t0+mloc); pair-symmetric [0, M)
@@ -55,50 +73,53 @@ static inline size_t qc_smem_bytes(int NT, int M, int mloc) {
 //   mirrored (t,x)    : partner t, tile YT[slab]     (pair-symmetric mode, t in the shard, t != x)
 // HBM/L2-bound (every tile is read once per orientation): 16-byte loads, 8 in flight per thread.
 template <int NT>
-__global__ void __launch_bounds__(QC_THREADS) k_qcontract(const QCParams p) {
+__global__ void __launch_bounds__(QC_THREADS, NT <= 2 ? 2 : 1) k_qcontract(const QCParams p) {
   constexpr int Np = NT * 8, Np2 = Np * Np;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   extern __shared__ double qc_smem[];
   double* red = qc_smem;                                         // [GROUPS][Np][ECHUNK]
   int* s_tile = reinterpret_cast<int*>(red + QC_GROUPS * Np * QC_ECHUNK);
   int* s_urow = s_tile + (p.M + p.mloc);
-  __shared__ int s_count;
-  const int tid = threadIdx.x, lane = tid & 31, M = p.M;
+  const int tid = threadIdx.x, M = p.M;
   const int x = p.row0 + blockIdx.x;
   const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
 
-  // ---- compacted term list (one warp, ballot prefix) ----
-  if (tid < 32) {
-    const int nterms = p.idxmap ? M + p.mloc : M;
-    int cnt = 0;
-    for (int base = 0; base < nterms; base += 32) {
-      const int n = base + lane;
-      int tile = -1, urow = 0;
-      if (n < nterms) {
-        if (n < M) {
-          if (mine) {
-            tile = p.idxmap ? __ldg(p.idxmap + (size_t)(x - p.t0) * M + n) : (x - p.t0) * M + n;
-            urow = n;
-          }
-        } else {
-          const int tl = n - M;
-          if (p.t0 + tl != x) {                  // the diagonal slab is already in the first list
-            tile = __ldg(p.idxmap + (size_t)tl * M + x);
-            if (tile >= 0) tile |= QC_TBIT;
-            urow = p.t0 + tl;
-          }
-        }
+  // ---- term list in closed form (no search, no compaction), all threads ----
+  //   own terms      i in [0, n_own)      : slab rowstart[x-t0] + i, partner q_i
+  //   mirrored terms t in shard, t != x, slab (t,x) selected: t < x with t = x (mod 2),
+  //                                                        t > x with t = x+1 (mod 2)
+  const int t1 = p.t0 + p.mloc;
+  int n_own = 0, n_lo = 0, n_hi = 0, lo_first = 0, hi_first = 0;
+  if (p.rowstart) {
+    if (mine) n_own = pair_row_count(x, M);
+    const int lo_end = min(x, t1);                       // t in [t0, lo_end), parity x&1
+    lo_first = p.t0 + (((x & 1) - (p.t0 & 1)) & 1);
+    n_lo = lo_end > lo_first ? (lo_end - lo_first + 1) >> 1 : 0;
+    const int hi_beg = max(x + 1, p.t0);                 // t in [hi_beg, t1), parity (x+1)&1
+    hi_first = hi_beg + ((((x + 1) & 1) - (hi_beg & 1)) & 1);
+    n_hi = t1 > hi_first ? (t1 - hi_first + 1) >> 1 : 0;
+  } else if (mine) {
+    n_own = M;
+  }
+  const int cnt = n_own + n_lo + n_hi;
+  for (int i = tid; i < cnt; i += QC_THREADS) {
+    int tile, urow;
+    if (i < n_own) {
+      if (p.rowstart) {
+        tile = __ldg(p.rowstart + (x - p.t0)) + i;
+        urow = pair_ith_q(x, i);
+      } else {
+        tile = (x - p.t0) * M + i;
+        urow = i;
       }
-      const bool v = tile >= 0;
-      const unsigned m = __ballot_sync(0xffffffffu, v);
-      if (v) {
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        s_tile[pos] = tile;
-        s_urow[pos] = urow;
-      }
-      cnt += __popc(m);
+    } else {
+      const int k = i - n_own;
+      const int t = k < n_lo ? lo_first + 2 * k : hi_first + 2 * (k - n_lo);
+      tile = (__ldg(p.rowstart + (t - p.t0)) + pair_rank(t, x)) | QC_TBIT;
+      urow = t;
     }
-    if (lane == 0) s_count = cnt;
+    s_tile[i] = tile;
+    s_urow[i] = urow;
   }
   __syncthreads();
 
@@ -109,7 +130,6 @@ __global__ void __launch_bounds__(QC_THREADS) k_qcontract(const QCParams p) {
   double acc[Np][2];
 #pragma unroll
   for (int j = 0; j < Np; ++j) acc[j][0] = acc[j][1] = 0.0;
-  const int cnt = s_count;
   const int per = (cnt + QC_GROUPS - 1) / QC_GROUPS;
   const int n0 = grp * per, n1 = min(cnt, n0 + per);
 
