@@ -18,7 +18,13 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("outer_"))
+
+
+def outer_golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "outer_*.npz")))
 
 
 def load_golden(name):

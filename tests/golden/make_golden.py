@@ -102,5 +102,50 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# outer-loop goldens: the exact-diagonalisation harness (esoo_b200.harness) driven by the LIVE
+# reference optimiser; the GPU test drives the same harness with the CUDA optimiser.
+# ------------------------------------------------------------------------------------------------
+OUTER_CASES = [
+    # name, M, N, n_alpha, n_beta, n_states, weights, outer maxiter, outer tol, (bb0, tol, maxiter)
+    ("outer_H2like_M8_N2", 8, 2, 1, 1, 1, None, 8, 1e-9, (1e-3, 1e-9, 2000)),
+    ("outer_H4like_M12_N4", 12, 4, 2, 2, 1, None, 6, 1e-9, (1e-3, 1e-9, 3000)),
+    ("outer_M10_N3", 10, 3, 2, 1, 1, None, 6, 1e-9, (1e-3, 1e-9, 3000)),
+    ("outer_excited_M8_N2_k2", 8, 2, 1, 1, 2, [2, 1], 6, 1e-9, (1e-3, 1e-9, 2000)),
+]
+
+
+def molecule_like(M, seed=0):
+    """Orbital-energy-like diagonal + weak couplings, PSD 8-fold-symmetric ERIs."""
+    gen = torch.Generator().manual_seed(1000 + seed)
+    eps = torch.linspace(-1.5, 1.0, M, dtype=torch.float64)
+    noise = 0.1 * torch.randn(M, M, generator=gen, dtype=torch.float64)
+    h = torch.diag(eps) + 0.5 * (noise + noise.T)
+    g = synthetic.eri_spatial(M, seed=synthetic.SEED_ERI + seed, rank=12, scale=0.6)
+    return synthetic.spin_orbital_integrals(h, g, "abba")
+
+
+def main_outer():
+    from esoo_b200 import harness
+    Pupo, _ = ref_loader.load_reference()
+    for (name, M, N, na, nb, k, weights, omax, otol, (bb0, tol, imax)) in OUTER_CASES:
+        hs, gs = molecule_like(M, seed=M + N)
+        solver = ref_loader.make_solver(True, weights)
+        opt = Pupo(initial_BBstepsize=bb0, stopping_tolerance=tol, maxiter=imax)
+        res = harness.run_outer_loop(opt, hs, gs, 2 * N, na, nb, maxiter=omax,
+                                     stopping_tolerance=otol, n_states=k, weights=weights,
+                                     energy_impl=solver.compute_rotated_energy)
+        E = np.array(res["energies"], dtype=np.float64)
+        print(f"{name}: outer iterations {len(E)}, energies {E[:, 0]}")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), M=M, N=N, n_alpha=na, n_beta=nb,
+                            n_states=k, weights=np.array(weights if weights else [1.0]),
+                            outer_maxiter=omax, outer_tol=otol, bb0=bb0, tol=tol, maxiter=imax,
+                            h_spin=hs.numpy(), g_spin=gs.numpy(), energies=E,
+                            U_final=res["U"].numpy())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] == "inner":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "outer":
+        main_outer()

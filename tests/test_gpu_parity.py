@@ -426,3 +426,37 @@ def test_full_size_properties(torch_cuda):
     assert abs(accE - float(E3)) <= 1e-10 * scale
     assert _rel(accg.cpu().numpy(), g3.cpu().numpy()) <= 1e-12
     eng.close()
+
+
+# --------------------------------------------------------------------------------------------
+# (d) the reference's outer loop (exact-diagonalisation stand-in for VQE):
+#     goldens produced with the LIVE reference optimiser on the CPU
+# --------------------------------------------------------------------------------------------
+from conftest import outer_golden_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", outer_golden_names())
+def test_outer_loop_vs_reference_golden(torch_cuda, name):
+    """Final (and every intermediate) outer-loop energy within 1e-8 Ha of the run that used the
+    reference optimiser; the rotated Hamiltonian comes from the CUDA transform (oo_transform)."""
+    import esoo_b200
+    from esoo_b200 import harness, ingest
+    torch = torch_cuda
+    gold = load_golden(name)
+    hs, gs = torch.from_numpy(gold["h_spin"]), torch.from_numpy(gold["g_spin"])
+    M, N, k = int(gold["M"]), int(gold["N"]), int(gold["n_states"])
+    weights = list(gold["weights"]) if k > 1 else None
+    h_sp, g_sp, _ = ingest.reduce_integrals(hs, gs)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h_sp, g_sp)
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(float(gold["bb0"]), float(gold["tol"]),
+                                                      int(gold["maxiter"]), device="cuda:0")
+    res = harness.run_outer_loop(opt, hs, gs, 2 * N, int(gold["n_alpha"]), int(gold["n_beta"]),
+                                 maxiter=int(gold["outer_maxiter"]),
+                                 stopping_tolerance=float(gold["outer_tol"]), n_states=k,
+                                 weights=weights, engine_for_transform=eng)
+    E = np.array(res["energies"])
+    assert E.shape == gold["energies"].shape, "different number of outer iterations"
+    assert np.max(np.abs(E - gold["energies"])) <= EFINAL_TOL
+    eng.close()
+    esoo_b200.clear_engine_cache()
