@@ -271,6 +271,18 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = K / float(e2e_t.item())
 
+    # ---------------- whole inner loop on the device (eval + all-reduce + retraction + BB + stop) --
+    n_inner = max(10, min(K, 50))
+    barrier()
+    t_c = time.perf_counter()
+    res = eng.optimize(U_host[0], 1e-3, 0.0, n_inner)      # tol=0: runs until iteration > maxiter
+    t_d = time.perf_counter()
+    inner_t = torch.tensor([t_d - t_c], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(inner_t, op=dist.ReduceOp.MAX)
+    inner_iters = res["n_iter"]
+    inner_rate = inner_iters / float(inner_t.item())
+
     if rank == 0:
         hbm_peak, peak_src = _load_peaks()
         dmma, dfma, stream_read = esoo_b200.measure_peaks(local, 4 << 30)
@@ -312,6 +324,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": M * N * 8,
                     "d2h_bytes_per_step": (M * N + 1) * 8,
                     "api": "OrbitalEngine.energy_grad_host -> oo_energy_grad_host (host buffers)"},
+            "inner_loop": {"iterations_per_s": inner_rate, "iterations": inner_iters,
+                           "what": "oo_optimize: device-resident loop of pupo.py:161-350, one "
+                                   "evaluation + retraction + BB step + stop test per iteration, "
+                                   "host round trip only every 4 iterations (flag poll)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "energy_checksum": e_sum,
