@@ -9,8 +9,9 @@
 //             U_{k+1} = orth(U_k - alpha G_k)                                  :157
 //   driver:   three hand-unrolled iterations then `while S[0] > tol and k <= maxiter`,
 //             S_k = (1-d)|dE| + d S_{k-1} with the one-step lag of the loop body   :176-350
-// The N x N symmetric eigenproblem (N <= 32) is solved by a cyclic two-sided Jacobi iteration in
-// shared memory (round-robin pairing, N/2 rotations in parallel).
+// (V^T V)^(-1/2) (N <= 32) comes from a coupled Newton-Schulz iteration in shared memory; if that
+// does not converge (very ill-conditioned Gram matrix) a cyclic two-sided Jacobi eigensolver
+// (round-robin pairing, N/2 rotations in parallel) takes over.
 #pragma once
 #include "oo_common.cuh"
 
@@ -112,40 +113,137 @@ __device__ inline void jacobi_eigh_smem(double* A, double* Q, double* cs, int n,
   }
 }
 
-// U_out = orth(V) for an M x N matrix V in global memory.  One CTA.  V and U_out may alias.
-// smem: sA, sQ, sS are (K3_NMAX)*(K3_NMAX+1) doubles each; cs 4*K3_NMAX doubles.
+// Z -> (A/c)^(-1/2) by the coupled Newton-Schulz iteration
+//     T = Z Y,  Y <- Y (3I - T)/2,  Z <- (3I - T) Z / 2,     Y0 = A/c, Z0 = I,
+// c = max row sum of |A| (>= lambda_max, so the spectrum of A/c lies in (0,1] and the iteration
+// converges; quadratically once ||I - T|| < 1).  Only N x N products: ~3 us where the Jacobi
+// eigensolver needs ~100 us.  Returns false if 60 iterations did not reach ||I - T||_F < 1e-8
+// (then the caller falls back to the eigensolver).  All threads of the CTA must call.
+__device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double* Z, double* W,
+                                             int n, double* scratch, double* inv_sqrt_c) {
+  constexpr int LD = K3_NMAX + 1;
+  constexpr int EPT = (K3_NMAX * K3_NMAX + K3_THREADS - 1) / K3_THREADS;  // elements per thread
+  const int tid = threadIdx.x, nth = blockDim.x, nn = n * n;
+  if (tid < n) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += fabs(A[tid * LD + j]);
+    scratch[tid] = s;
+  }
+  __syncthreads();
+  double c = 0.0;
+  for (int i = 0; i < n; ++i) c = fmax(c, scratch[i]);
+  __syncthreads();
+  const double inv_c = 1.0 / c;
+  for (int idx = tid; idx < nn; idx += nth) {
+    const int i = idx / n, j = idx - i * n;
+    Y[i * LD + j] = A[i * LD + j] * inv_c;
+    Z[i * LD + j] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  bool converged = false;
+  for (int it = 0; it < 60; ++it) {
+    double r = 0.0;
+    for (int idx = tid; idx < nn; idx += nth) {
+      const int i = idx / n, j = idx - i * n;
+      double s = 0.0;
+      for (int m = 0; m < n; ++m) s = fma(Z[i * LD + m], Y[m * LD + j], s);
+      const double d = s - ((i == j) ? 1.0 : 0.0);
+      r = fma(d, d, r);
+      W[i * LD + j] = ((i == j) ? 3.0 : 0.0) - s;
+    }
+    r = block_sum(r, scratch);  // syncs: W is complete afterwards
+    double yv[EPT], zv[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const int idx = tid + k * nth;
+      yv[k] = zv[k] = 0.0;
+      if (idx < nn) {
+        const int i = idx / n, j = idx - i * n;
+        double sy = 0.0, sz = 0.0;
+        for (int m = 0; m < n; ++m) {
+          sy = fma(Y[i * LD + m], W[m * LD + j], sy);
+          sz = fma(W[i * LD + m], Z[m * LD + j], sz);
+        }
+        yv[k] = 0.5 * sy;
+        zv[k] = 0.5 * sz;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const int idx = tid + k * nth;
+      if (idx < nn) {
+        const int i = idx / n, j = idx - i * n;
+        Y[i * LD + j] = yv[k];
+        Z[i * LD + j] = zv[k];
+      }
+    }
+    __syncthreads();
+    if (r < 1e-16) {  // ||I - T||_F < 1e-8 before this update => ~1e-16 after it
+      converged = true;
+      break;
+    }
+  }
+  *inv_sqrt_c = 1.0 / sqrt(c);
+  return converged;
+}
+
+// U_out = orth(V) = V (V^T V)^(-1/2) for an M x N matrix V in global memory.  One CTA.  V and
+// U_out may alias.  smem: sA, sB1, sB2, sB3 are K3_NMAX*(K3_NMAX+1) doubles each; cs 4*K3_NMAX;
+// scratch 32 doubles.
 __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
-                                   double* sQ, double* sS, double* cs, int* sflag) {
+                                   double* sB1, double* sB2, double* sB3, double* cs,
+                                   double* scratch, int* sflag) {
   constexpr int LD = K3_NMAX + 1;
   const int tid = threadIdx.x, nth = blockDim.x;
   // Gram matrix V^T V (upper triangle computed, mirrored)
   for (int idx = tid; idx < N * N; idx += nth) {
     const int i = idx / N, j = idx - i * N;
     if (j >= i) {
-      double s = 0.0;
-      for (int t = 0; t < M; ++t) s = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s);
+      double s0 = 0.0, s1 = 0.0;
+      int t = 0;
+#pragma unroll 4
+      for (; t + 1 < M; t += 2) {
+        s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
+        s1 = fma(V[(size_t)(t + 1) * N + i], V[(size_t)(t + 1) * N + j], s1);
+      }
+      if (t < M) s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
+      const double s = s0 + s1;
       sA[i * LD + j] = s;
       sA[j * LD + i] = s;
     }
   }
   __syncthreads();
-  jacobi_eigh_smem(sA, sQ, cs, N, sflag);
-  __syncthreads();
-  // S = Q diag(w^-1/2) Q^T
-  for (int idx = tid; idx < N * N; idx += nth) {
-    const int i = idx / N, j = idx - i * N;
-    double s = 0.0;
-    for (int m = 0; m < N; ++m) s += sQ[i * LD + m] * sQ[j * LD + m] / sqrt(sA[m * LD + m]);
-    sS[i * LD + j] = s;
+  double scale = 1.0;
+  double* S = sB2;  // inverse square root (up to `scale`) ends up here
+  const bool ok = newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale);
+  if (!ok) {
+    // robust path: S = Q diag(w^-1/2) Q^T from the Jacobi eigen-decomposition (reference:
+    // torch.linalg.eigh, partial_unitary_projection_optimizer.py:80-81)
+    for (int idx = tid; idx < N * N; idx += nth) {
+      const int i = idx / N, j = idx - i * N;
+      sB1[i * LD + j] = sA[i * LD + j];
+    }
+    __syncthreads();
+    jacobi_eigh_smem(sB1, sB3, cs, N, sflag);
+    __syncthreads();
+    for (int idx = tid; idx < N * N; idx += nth) {
+      const int i = idx / N, j = idx - i * N;
+      double s = 0.0;
+      for (int m = 0; m < N; ++m)
+        s += sB3[i * LD + m] * sB3[j * LD + m] / sqrt(sB1[m * LD + m]);
+      sB2[i * LD + j] = s;
+    }
+    scale = 1.0;
+    __syncthreads();
   }
-  __syncthreads();
   // U = V S ; row-wise so V and Uout may alias (each thread owns whole rows)
   for (int t = tid; t < M; t += nth) {
     double v[K3_NMAX];
-    for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j];
+    for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j] * scale;
     for (int j = 0; j < N; ++j) {
       double s = 0.0;
-      for (int m = 0; m < N; ++m) s = fma(v[m], sS[m * LD + j], s);
+      for (int m = 0; m < N; ++m) s = fma(v[m], S[m * LD + j], s);
       Uout[(size_t)t * N + j] = s;
     }
   }
@@ -153,10 +251,10 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
 }
 
 __global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uout, int M, int N) {
-  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
-      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX];
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
   __shared__ int sflag;
-  retract_cta(V, Uout, M, N, sA, sQ, sS, cs, &sflag);
+  retract_cta(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
 }
 
 struct StepParams {
@@ -173,8 +271,8 @@ struct StepParams {
 
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
 __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
-  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
-      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
   __shared__ int sflag;
   OptState* st = p.st;
   if (st->done) return;
@@ -242,7 +340,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
     p.Gprev[i] = g;
   }
   __syncthreads();
-  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sQ, sS, cs, &sflag);
+  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
@@ -258,8 +356,8 @@ struct BBParams {
   double* Unew; double* Vtmp; double* alpha_io; int iteration; int M, N;
 };
 __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
-  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sQ[K3_NMAX * (K3_NMAX + 1)],
-      sS[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
   __shared__ int sflag;
   const int tid = threadIdx.x, nth = blockDim.x, MN = p.M * p.N;
   double alpha = *p.alpha_io;
@@ -280,7 +378,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   }
   for (int i = tid; i < MN; i += nth) p.Vtmp[i] = p.Ucur[i] - alpha * p.Gcur[i];
   __syncthreads();
-  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sQ, sS, cs, &sflag);
+  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
   if (tid == 0) *p.alpha_io = alpha;
 }
 
