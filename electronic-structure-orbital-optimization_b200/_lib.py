@@ -17,6 +17,7 @@ SYMBOLS = [
     "oo_energy_grad_host", "oo_transform", "oo_orth", "oo_bb_update", "oo_optimize",
     "oo_nccl_unique_id", "oo_comm_init", "oo_allreduce", "oo_set_timing", "oo_last_timing",
     "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
+    "oo_ingest_spin_g", "oo_set_rdms_spin",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -87,6 +88,8 @@ def load() -> C.CDLL:
     lib.oo_measure_peaks.argtypes = [C.c_int, sz, dp]
     lib.oo_set_pair_symmetry.argtypes = [vp, C.c_int]
     lib.oo_streamed_slabs.argtypes = [vp]
+    lib.oo_ingest_spin_g.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.POINTER(C.c_uint), dp]
+    lib.oo_set_rdms_spin.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), dp, C.c_int, C.c_uint]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("oo_device_count",):

@@ -115,7 +115,7 @@ struct oo_ctx {
   double *Y = nullptr, *T3 = nullptr, *Gp = nullptr, *D = nullptr, *A = nullptr, *UD = nullptr,
          *UDt = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
          *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr,
-         *YT = nullptr, *Upad = nullptr, *B1 = nullptr, *B12 = nullptr;
+         *YT = nullptr, *Upad = nullptr, *B1 = nullptr, *B12 = nullptr, *Gtmp = nullptr;
   cudaStream_t aux = nullptr;       // one-body terms run here, concurrently with K1
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int hist_cap = 0;
@@ -410,6 +410,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->Y, (size_t)mloc * M * Np2);
   A(&c->YT, (size_t)mloc * (M / 2 + 1) * Np2);
   A(&c->Upad, (size_t)M * c->Np);
+  A(&c->Gtmp, (size_t)N * N * N * N);
   A(&c->B1, (size_t)mloc * N);
   A(&c->B12, (size_t)mloc * N);
   A(&c->T3, (size_t)M * c->Np * Np2);
@@ -475,7 +476,7 @@ int oo_destroy(oo_ctx* c) {
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
-                    c->YT,  c->Upad, c->B1,    c->B12};
+                    c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (c->counter) cudaFree(c->counter);
@@ -563,6 +564,82 @@ int oo_set_rdms(oo_ctx* c, const double* D_dev, const double* G_dev) {
   k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp, c->N, c->Np, 1);
   CU_TRY(cudaGetLastError());
   c->launches++;
+  c->have_rdms = true;
+  return OO_OK;
+}
+
+int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
+                     double* g_sp_out_dev, unsigned* block_mask, double* stats_host) {
+  if (!g_spin_dev || !g_sp_out_dev || !block_mask || M < 1)
+    return fail(OO_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  CU_TRY(cudaMalloc((void**)&d, 32 * sizeof(unsigned long long)));
+  CU_TRY(cudaMemset(d, 0, 32 * sizeof(unsigned long long)));
+  k_spin_block_maxabs<<<148 * 4, 256>>>(g_spin_dev, M, d);
+  unsigned long long bits[32];
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(bits, d, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(OO_ERR_CUDA, "spin-block scan: %s", cudaGetErrorString(e));
+  }
+  double bmax[16], gmax = 0.0;
+  memcpy(bmax, bits, sizeof bmax);
+  for (int b = 0; b < 16; ++b) gmax = std::max(gmax, bmax[b]);
+  unsigned mask = 0;
+  int ref = -1;
+  for (int b = 0; b < 16; ++b)
+    if (bmax[b] > rtol * (gmax > 0 ? gmax : 1.0)) {
+      mask |= 1u << b;
+      if (ref < 0) ref = b;
+    }
+  if (ref < 0) ref = 0;  // all-zero tensor: take the alpha-alpha-alpha-alpha block
+  k_spin_block_extract<<<148 * 4, 256>>>(g_spin_dev, M, ref, mask, g_sp_out_dev, d + 16);
+  e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpy(bits, d + 16, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(OO_ERR_CUDA, "spin-block extract: %s", cudaGetErrorString(e));
+  double dmax[16], dev_max = 0.0;
+  memcpy(dmax, bits, sizeof dmax);
+  for (int b = 0; b < 16; ++b) dev_max = std::max(dev_max, dmax[b]);
+  *block_mask = mask;
+  if (stats_host) {
+    stats_host[0] = gmax;
+    stats_host[1] = dev_max;
+  }
+  if (dev_max > rtol * (gmax > 0 ? gmax : 1.0))
+    return fail(OO_ERR_UNSUPPORTED,
+                "unrestricted two-body integrals: non-zero spin blocks differ (max deviation %.3e, "
+                "max |g| %.3e)", dev_max, gmax);
+  return OO_OK;
+}
+
+int oo_set_rdms_spin(oo_ctx* c, const double* const* D_spin_dev, const double* const* G_spin_dev,
+                     const double* weights_host, int nstates, unsigned block_mask) {
+  if (!c || !D_spin_dev || !G_spin_dev || nstates < 1)
+    return fail(OO_ERR_INVALID, "bad argument");
+  if (nstates > 8) return fail(OO_ERR_UNSUPPORTED, "at most 8 states per call (got %d)", nstates);
+  CU_TRY(cudaSetDevice(c->device));
+  RdmSpinParams rp;
+  memset(&rp, 0, sizeof rp);
+  for (int n = 0; n < nstates; ++n) {
+    if (!D_spin_dev[n] || !G_spin_dev[n]) return fail(OO_ERR_INVALID, "NULL RDM pointer");
+    rp.D[n] = D_spin_dev[n];
+    rp.G[n] = G_spin_dev[n];
+    rp.w[n] = weights_host ? weights_host[n] : 1.0;
+  }
+  rp.nstates = nstates;
+  rp.N = c->N;
+  rp.mask = block_mask;
+  const size_t N4 = (size_t)c->N * c->N * c->N * c->N;
+  const int grid = (int)std::min<size_t>((N4 + 255) / 256, 148 * 8);
+  k_rdm_spin_sum<<<grid, 256, 0, c->stream>>>(rp, c->D, c->Gtmp);
+  CU_TRY(cudaGetLastError());
+  k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(c->Gtmp, c->Gp, c->N, c->Np, 1);
+  CU_TRY(cudaGetLastError());
+  c->launches += 2;
   c->have_rdms = true;
   return OO_OK;
 }

@@ -58,3 +58,102 @@ __global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict
 }
 
 }  // namespace oo
+
+namespace oo {
+
+// ---------------------------------------------------------------------------------------------
+// Spin-orbital -> spatial ingest of the reference's tensors (extent P = 2M / Q = 2N, alpha block
+// first): base_opt_orb_solver.py:549 makes W = block_diag(U,U), so the energy only sees g and
+// Gamma through matching spin blocks.  Block id b = 8*s0 + 4*s1 + 2*s2 + s3.
+// ---------------------------------------------------------------------------------------------
+
+// stats[b] = max |g[block b]| (bit pattern, atomicMax);  grid-stride over the P^4 elements.
+__global__ void k_spin_block_maxabs(const double* __restrict__ g, int M, unsigned long long* stats) {
+  const size_t P = 2 * (size_t)M, total = P * P * P * P;
+  __shared__ unsigned long long s_max[16];
+  if (threadIdx.x < 16) s_max[threadIdx.x] = 0ull;
+  __syncthreads();
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % P), r = (int)((idx / P) % P), q = (int)((idx / (P * P)) % P),
+              p = (int)(idx / (P * P * P));
+    const int b = 8 * (p >= M) + 4 * (q >= M) + 2 * (r >= M) + (s >= M);
+    const double v = fabs(g[idx]);
+    if (v != 0.0) atomicMax(&s_max[b], (unsigned long long)__double_as_longlong(v));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && s_max[threadIdx.x]) atomicMax(stats + threadIdx.x, s_max[threadIdx.x]);
+}
+
+// out[pqrs] = g[block ref](pqrs) and diff[b] = max |g[block b] - g[block ref]| for blocks in mask.
+__global__ void k_spin_block_extract(const double* __restrict__ g, int M, int ref, unsigned mask,
+                                     double* __restrict__ out, unsigned long long* diff) {
+  const size_t P = 2 * (size_t)M, M4 = (size_t)M * M * M * M;
+  const size_t P3 = P * P * P, P2 = P * P;
+  double dmax[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) dmax[b] = 0.0;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M4;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % M), r = (int)((idx / M) % M), q = (int)((idx / ((size_t)M * M)) % M),
+              p = (int)(idx / ((size_t)M * M * M));
+    auto at = [&](int b) {
+      return g[(size_t)(p + M * ((b >> 3) & 1)) * P3 + (size_t)(q + M * ((b >> 2) & 1)) * P2 +
+               (size_t)(r + M * ((b >> 1) & 1)) * P + (size_t)(s + M * (b & 1))];
+    };
+    const double v = at(ref);
+    out[idx] = v;
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+      if ((mask >> b) & 1u) dmax[b] = fmax(dmax[b], fabs(at(b) - v));
+  }
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    double v = dmax[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v != 0.0)
+      atomicMax(diff + b, (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+// Spatial, state-weighted RDMs from spin-orbital ones:
+//   D~[i][j]       = sum_n w_n (D_n[i,j] + D_n[N+i,N+j])
+//   G~[i][j][k][l] = sum_n w_n sum_{b in mask} G_n[block b](i,j,k,l)
+struct RdmSpinParams {
+  const double* D[8];
+  const double* G[8];
+  double w[8];
+  int nstates, N;
+  unsigned mask;
+};
+__global__ void k_rdm_spin_sum(const RdmSpinParams p, double* __restrict__ Dout,
+                               double* __restrict__ Gout) {
+  const int N = p.N;
+  const size_t Q = 2 * (size_t)N, Q2 = Q * Q, Q3 = Q2 * Q;
+  const size_t N4 = (size_t)N * N * N * N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < N4;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int l = (int)(idx % N), k = (int)((idx / N) % N), j = (int)((idx / ((size_t)N * N)) % N),
+              i = (int)(idx / ((size_t)N * N * N));
+    double acc = 0.0;
+    for (int n = 0; n < p.nstates; ++n) {
+      double s = 0.0;
+      for (int b = 0; b < 16; ++b)
+        if ((p.mask >> b) & 1u)
+          s += p.G[n][(size_t)(i + N * ((b >> 3) & 1)) * Q3 + (size_t)(j + N * ((b >> 2) & 1)) * Q2 +
+                      (size_t)(k + N * ((b >> 1) & 1)) * Q + (size_t)(l + N * (b & 1))];
+      acc = fma(p.w[n], s, acc);
+    }
+    Gout[idx] = acc;
+    if (idx < (size_t)N * N) {
+      const int a = (int)(idx / N), c = (int)(idx % N);
+      double d = 0.0;
+      for (int n = 0; n < p.nstates; ++n)
+        d = fma(p.w[n], p.D[n][(size_t)a * Q + c] + p.D[n][(size_t)(a + N) * Q + (c + N)], d);
+      Dout[idx] = d;
+    }
+  }
+}
+
+}  // namespace oo

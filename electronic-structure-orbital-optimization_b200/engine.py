@@ -132,6 +132,27 @@ class OrbitalEngine:
         _lib.check(self.lib.oo_set_rdms(self._ctx, _ptr(D), _ptr(G)))
         _lib.check(self.lib.oo_synchronize(self._ctx))   # D, G may be freed by the caller now
 
+    def set_rdms_spin(self, oneRDMs, twoRDMs, weights, block_mask: int) -> None:
+        """Spin-orbital RDMs (lists of [2N,2N] / [2N]^4 tensors) -> spatial, weighted, symmetrised
+        copies inside the library, all on the device (k_rdm_spin_sum + k_prepare_gamma)."""
+        Q = 2 * self.N
+        ones = [_dev_f64(d, self.device) for d in oneRDMs]
+        twos = [_dev_f64(g, self.device) for g in twoRDMs]
+        for d, g in zip(ones, twos):
+            if tuple(d.shape) != (Q, Q) or tuple(g.shape) != (Q,) * 4:
+                raise ValueError(f"bad spin-orbital RDM shapes {tuple(d.shape)} {tuple(g.shape)}")
+        if len(ones) != len(twos) or len(weights) != len(ones):
+            raise ValueError("number of states / weights mismatch")
+        if len(ones) > 8:
+            raise NotImplementedError("more than 8 states per call")
+        n = len(ones)
+        Dp = (C.c_void_p * n)(*[d.data_ptr() for d in ones])
+        Gp = (C.c_void_p * n)(*[g.data_ptr() for g in twos])
+        w = (C.c_double * n)(*[float(x) for x in weights])
+        self._inputs_ready()
+        _lib.check(self.lib.oo_set_rdms_spin(self._ctx, Dp, Gp, w, n, int(block_mask)))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+
     def set_pair_symmetry(self, enable: bool) -> None:
         """Stream one slab of every pair {(t,q),(q,t)} (default) or every slab of the shard."""
         _lib.check(self.lib.oo_set_pair_symmetry(self._ctx, 1 if enable else 0))

@@ -70,6 +70,49 @@ def reduce_integrals(h: torch.Tensor, g: torch.Tensor, rtol: float = 1e-12):
     return h_sp.contiguous(), g_sp.contiguous(), SpinStructure(M=M, blocks=blocks)
 
 
+def block_mask(structure: SpinStructure) -> int:
+    """Bit b = 8*s0 + 4*s1 + 2*s2 + s3 for every non-zero spin block (C-ABI convention)."""
+    m = 0
+    for s0, s1, s2, s3 in structure.blocks:
+        m |= 1 << (8 * s0 + 4 * s1 + 2 * s2 + s3)
+    return m
+
+
+def reduce_integrals_device(h: torch.Tensor, g: torch.Tensor, rtol: float = 1e-12):
+    """Same contract as reduce_integrals for CUDA tensors, with the P^4 scan, the block
+    comparison and the extraction done by the library's kernels (oo_ingest_spin_g)."""
+    import ctypes as C
+    from . import _lib
+    if not g.is_cuda:
+        raise ValueError("reduce_integrals_device needs CUDA tensors")
+    if h.dtype != torch.float64 or g.dtype != torch.float64:
+        raise TypeError("integrals must be float64 (complex / lower precision is not supported)")
+    P = h.shape[0]
+    if h.dim() != 2 or g.dim() != 4 or tuple(g.shape) != (P,) * 4 or h.shape[1] != P or P % 2:
+        raise ValueError(f"expected h [P,P] and g [P,P,P,P], got {tuple(h.shape)} {tuple(g.shape)}")
+    M = P // 2
+    scale_h = float(h.abs().max()) or 1.0
+    if float(_blk(h, M, (0, 1)).abs().max()) > rtol * scale_h or \
+            float(_blk(h, M, (1, 0)).abs().max()) > rtol * scale_h:
+        raise NotImplementedError("one-body integrals couple alpha and beta orbitals")
+    h_sp = _blk(h, M, (0, 0)).contiguous()
+    if float((_blk(h, M, (1, 1)) - h_sp).abs().max()) > rtol * scale_h:
+        raise NotImplementedError("unrestricted one-body integrals (h_aa != h_bb) are not supported")
+    g = g.contiguous()
+    g_sp = torch.empty(M, M, M, M, dtype=torch.float64, device=g.device)
+    mask = C.c_uint(0)
+    stats = (C.c_double * 2)()
+    torch.cuda.current_stream(g.device).synchronize()
+    lib = _lib.load()
+    rc = lib.oo_ingest_spin_g(g.device.index, C.c_void_p(g.data_ptr()), M, float(rtol),
+                              C.c_void_p(g_sp.data_ptr()), C.byref(mask), stats)
+    if rc == -5:
+        raise NotImplementedError(lib.oo_last_error().decode())
+    _lib.check(rc)
+    blocks = [tuple((b >> s) & 1 for s in (3, 2, 1, 0)) for b in range(16) if (mask.value >> b) & 1]
+    return h_sp, g_sp, SpinStructure(M=M, blocks=blocks)
+
+
 def reduce_rdms(oneRDM, twoRDM, structure: SpinStructure, weights=None):
     """Spin-sum (and state-average with `weights`) the reference's RDM arguments.
 

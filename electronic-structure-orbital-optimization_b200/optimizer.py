@@ -115,7 +115,7 @@ class PartialUnitaryProjectionOptimizer:
         hit = _ENGINE_CACHE.get(key)
         if hit is not None:
             return hit
-        h_sp, g_sp, structure = ingest.reduce_integrals(h_dev, g_dev)
+        h_sp, g_sp, structure = ingest.reduce_integrals_device(h_dev, g_dev)
         while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
             old_key = next(iter(_ENGINE_CACHE))
             _ENGINE_CACHE.pop(old_key)[0].close()
@@ -140,8 +140,19 @@ class PartialUnitaryProjectionOptimizer:
         dev = self._torch_device()
         ones = [d.to(dev) for d in oneRDM] if weights is not None else oneRDM.to(dev)
         twos = [g.to(dev) for g in twoRDM] if weights is not None else twoRDM.to(dev)
-        D_sp, G_sp = ingest.reduce_rdms(ones, twos, structure, weights)
-        eng.set_rdms(D_sp, G_sp)
+        for t in (ones if weights is not None else [ones]) + (twos if weights is not None else [twos]):
+            if t.is_complex():
+                raise NotImplementedError(
+                    "complex RDMs (base_opt_orb_solver.py:565-580) are not supported")
+        if weights is not None and len(weights) != len(ones):
+            raise ValueError("number of weights does not match the number of states")
+        if weights is None:
+            eng.set_rdms_spin([ones], [twos], [1.0], ingest.block_mask(structure))
+        elif len(ones) <= 8:
+            eng.set_rdms_spin(ones, twos, weights, ingest.block_mask(structure))
+        else:                                   # rare: many states, spin-sum with torch instead
+            D_sp, G_sp = ingest.reduce_rdms(ones, twos, structure, weights)
+            eng.set_rdms(D_sp, G_sp)
         return eng
 
     # -- methods of the reference --------------------------------------------------------------

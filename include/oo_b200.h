@@ -82,6 +82,22 @@ int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_hos
  * (weights are folded in by the caller: E is linear in the RDMs). */
 int oo_set_rdms(oo_ctx* ctx, const double* D_dev, const double* G_dev);
 
+/* Spin-orbital ingest of the reference's two-body tensor g_spin_dev [P]^4, P = 2M (alpha block
+ * first; base.py:89-90).  Because W = block_diag(U,U) (base.py:549) the energy only couples
+ * matching spin blocks; block id b = 8*s0 + 4*s1 + 2*s2 + s3.  Finds the non-zero blocks
+ * (|.| > rtol * max|g|), verifies that they are identical (restricted integrals) and copies the
+ * common spatial tensor to g_sp_out_dev [M]^4.  *block_mask gets one bit per non-zero block;
+ * stats_host[0] = max|g|, stats_host[1] = max deviation between non-zero blocks.
+ * OO_ERR_UNSUPPORTED when the blocks differ (unrestricted integrals). */
+int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
+                     double* g_sp_out_dev, unsigned* block_mask, double* stats_host);
+/* RDMs straight from the reference's spin-orbital tensors (base.py:362-532 layout): nstates (<=8)
+ * device tensors D_n [2N][2N], G_n [2N]^4 given as HOST arrays of device pointers, host weights
+ * (NULL = 1): D~ = sum_n w_n (D_n[aa] + D_n[bb]), G~ = sum_n w_n sum_{b in block_mask} G_n[block b]
+ * (eig.py:149-169: the weighted energy sum is linear in the RDMs), then as oo_set_rdms. */
+int oo_set_rdms_spin(oo_ctx* ctx, const double* const* D_spin_dev, const double* const* G_spin_dev,
+                     const double* weights_host, int nstates, unsigned block_mask);
+
 /* Pair-symmetric slab mode (default: enabled).  A V4-symmetric tensor satisfies
  * g[t,q,r,s] = g[q,t,s,r], so the half-transformed tiles obey Y[q,t] = Y[t,q]^T: only one slab of
  * every pair {(t,q),(q,t)} is streamed from HBM (checkerboard choice: ~M/2 slabs per row, shards
