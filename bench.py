@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--M", type=int, default=M_BENCH)
     ap.add_argument("--N", type=int, default=N_BENCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU: all-reduce fused into the tail kernel over NVLink peer "
+                         "memory (default) or a separate NCCL call")
     ap.add_argument("--dense", action="store_true",
                     help="stream every slab of the shard instead of one per (t,q)/(q,t) pair")
     args = ap.parse_args()
@@ -197,6 +200,8 @@ def main():
     else:
         eng.set_integrals(h, g, assume_v4_symmetric=True)   # symmetric by construction
         esoo_b200.attach_nccl(eng)
+        if args.allreduce == "fused":
+            esoo_b200.attach_peer_memory(eng)
     eng.set_rdms(D, G)
     eng.set_pair_symmetry(not args.dense)
     slabs = eng.streamed_slabs()
@@ -307,6 +312,9 @@ def main():
                        "slabs_streamed_per_eval_per_gpu": slabs,
                        "eri_bytes_streamed_per_eval_per_gpu": alg_bytes,
                        "sharding": f"ERI first index over {world} GPU(s), rows/GPU={mloc}",
+                       "allreduce": "none (1 GPU)" if world == 1 else
+                       ("one-shot all-reduce fused into k_tail_row over NVLink peer memory"
+                        if args.allreduce == "fused" else "NCCL all-reduce of M*N+1 doubles"),
                        "cache": "ERI shard (>=4.3 GB) is larger than the 126 MB L2 and a fresh U "
                                 "is used every step; no explicit L2 flush"},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",

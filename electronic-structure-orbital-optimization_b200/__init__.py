@@ -6,7 +6,7 @@ include/oo_b200.h); this package is the host-side mirror of the reference interf
 from . import _lib, distributed, ingest, synthetic
 from .engine import OrbitalEngine, measure_peaks
 from .optimizer import PartialUnitaryProjectionOptimizer, clear_engine_cache
-from .distributed import shard_range, attach_nccl
+from .distributed import shard_range, attach_nccl, attach_peer_memory
 
 __all__ = ["PartialUnitaryProjectionOptimizer", "OrbitalEngine", "measure_peaks", "shard_range",
-           "attach_nccl", "clear_engine_cache", "ingest", "synthetic"]
+           "attach_nccl", "attach_peer_memory", "clear_engine_cache", "ingest", "synthetic"]

@@ -17,7 +17,8 @@ SYMBOLS = [
     "oo_energy_grad_host", "oo_transform", "oo_orth", "oo_bb_update", "oo_optimize",
     "oo_nccl_unique_id", "oo_comm_init", "oo_allreduce", "oo_set_timing", "oo_last_timing",
     "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
-    "oo_ingest_spin_g", "oo_set_rdms_spin",
+    "oo_ingest_spin_g", "oo_set_rdms_spin", "oo_energy_grad_allreduce", "oo_peer_export",
+    "oo_peer_attach", "oo_peer_status",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -73,6 +74,10 @@ def load() -> C.CDLL:
     lib.oo_set_rdms.argtypes = [vp, vp, vp]
     lib.oo_energy_grad.argtypes = [vp, vp, vp]
     lib.oo_energy_grad_host.argtypes = [vp, vp, vp, vp]
+    lib.oo_energy_grad_allreduce.argtypes = [vp, vp, vp]
+    lib.oo_peer_export.argtypes = [vp, vp]
+    lib.oo_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.oo_peer_status.argtypes = [vp]
     lib.oo_transform.argtypes = [vp, vp, vp, vp]
     lib.oo_orth.argtypes = [vp, vp, vp]
     lib.oo_bb_update.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]

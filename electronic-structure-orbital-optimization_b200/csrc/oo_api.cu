@@ -133,6 +133,13 @@ struct oo_ctx {
   // NCCL
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // fused peer-memory all-reduce (CUDA IPC)
+  void* peer_base = nullptr;            // my flags|slots allocation
+  void* peer_map[PEER_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peer_on = false;
+  int peer_stride = 0;
+  unsigned long long peer_seq = 0;
+  int* peer_err = nullptr;
   // timing
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -248,8 +255,21 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
 }
 
 template <int NT>
-int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag) {
+int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused) {
   TailParams tp;
+  memset(&tp.comm, 0, sizeof tp.comm);
+  if (fused) {
+    tp.comm.enabled = 1;
+    tp.comm.rank = c->rank;
+    tp.comm.world = c->world;
+    tp.comm.stride = c->peer_stride;
+    tp.comm.seq = ++c->peer_seq;
+    tp.comm.error_flag = c->peer_err;
+    for (int r = 0; r < c->world; ++r) {
+      tp.comm.flags[r] = (unsigned long long*)c->peer_map[r];
+      tp.comm.slots[r] = (double*)((char*)c->peer_map[r] + 256);
+    }
+  }
   tp.T3 = c->T3;
   tp.Gp = c->Gp;
   tp.U = U;
@@ -273,12 +293,12 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag)
   return OO_OK;
 }
 
-int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag) {
+int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused) {
   switch (c->NT) {
-    case 1: return launch_tail_t<1>(c, U, out, done_flag);
-    case 2: return launch_tail_t<2>(c, U, out, done_flag);
-    case 3: return launch_tail_t<3>(c, U, out, done_flag);
-    case 4: return launch_tail_t<4>(c, U, out, done_flag);
+    case 1: return launch_tail_t<1>(c, U, out, done_flag, fused);
+    case 2: return launch_tail_t<2>(c, U, out, done_flag, fused);
+    case 3: return launch_tail_t<3>(c, U, out, done_flag, fused);
+    case 4: return launch_tail_t<4>(c, U, out, done_flag, fused);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -294,7 +314,11 @@ int launch_qc(oo_ctx* c, const int* done_flag) {
 }
 
 // One evaluation: shard rows of dE/dU and partial E into `out` (device, M*N+1).
-int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) {
+int do_allreduce(oo_ctx* c, double* buf, size_t count);
+
+// reduce = false: this GPU's partial only.  reduce = true: the sum over all GPUs, through the
+// all-reduce fused into the tail kernel (peer memory) when attached, else through NCCL.
+int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, bool reduce) {
   if (!c->have_ints) return fail(OO_ERR_STATE, "oo_set_integrals has not been called");
   if (!c->have_rdms) return fail(OO_ERR_STATE, "oo_set_rdms has not been called");
   const bool tm = c->timing;
@@ -324,8 +348,11 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag) 
   if ((rc = launch_qc(c, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
   CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));   // join
-  if ((rc = launch_tail(c, U, out, done_flag))) return rc;
+  const bool fused = reduce && c->peer_on && c->world > 1;
+  if ((rc = launch_tail(c, U, out, done_flag, fused))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
+  if (reduce && !fused && c->world > 1)
+    return do_allreduce(c, out, (size_t)c->M * c->N + 1);
   return OO_OK;
 }
 
@@ -474,6 +501,10 @@ int oo_destroy(oo_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
+  for (int r = 0; r < PEER_MAX; ++r)
+    if (c->peer_map[r] && c->peer_map[r] != c->peer_base) cudaIpcCloseMemHandle(c->peer_map[r]);
+  if (c->peer_base) cudaFree(c->peer_base);
+  if (c->peer_err) cudaFree(c->peer_err);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
                     c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};
@@ -647,7 +678,13 @@ int oo_set_rdms_spin(oo_ctx* c, const double* const* D_spin_dev, const double* c
 int oo_energy_grad(oo_ctx* c, const double* U_dev, double* out_dev) {
   if (!c || !U_dev) return fail(OO_ERR_INVALID, "NULL argument");
   CU_TRY(cudaSetDevice(c->device));
-  return enqueue_eval(c, U_dev, out_dev ? out_dev : c->out, nullptr);
+  return enqueue_eval(c, U_dev, out_dev ? out_dev : c->out, nullptr, false);
+}
+
+int oo_energy_grad_allreduce(oo_ctx* c, const double* U_dev, double* out_dev) {
+  if (!c || !U_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  return enqueue_eval(c, U_dev, out_dev ? out_dev : c->out, nullptr, true);
 }
 
 int oo_energy_grad_host(oo_ctx* c, const double* U_host, double* E_host, double* grad_host) {
@@ -656,9 +693,8 @@ int oo_energy_grad_host(oo_ctx* c, const double* U_host, double* E_host, double*
   const size_t MN = (size_t)c->M * c->N;
   memcpy(c->pin, U_host, MN * sizeof(double));
   CU_TRY(cudaMemcpyAsync(c->Ucur, c->pin, MN * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  int rc = enqueue_eval(c, c->Ucur, c->out, nullptr);
+  int rc = enqueue_eval(c, c->Ucur, c->out, nullptr, true);
   if (rc) return rc;
-  if ((rc = do_allreduce(c, c->out, MN + 1))) return rc;
   CU_TRY(cudaMemcpyAsync(c->pin, c->out, (MN + 1) * sizeof(double), cudaMemcpyDeviceToHost,
                          c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
@@ -778,8 +814,7 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   auto enqueue_chunk = [&](int s) -> int {
     int rc;
     for (int i = 0; i < chunk; ++i) {
-      if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag))) return rc;
-      if ((rc = do_allreduce(c, c->out, MN + 1))) return rc;
+      if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag, true))) return rc;
       k_step<<<1, K3_THREADS, 0, c->stream>>>(sp);
       CU_TRY(cudaGetLastError());
       c->launches++;
@@ -850,6 +885,57 @@ int oo_comm_init(oo_ctx* c, const void* id128_host, int rank, int world) {
   c->rank = rank;
   c->world = world;
   return OO_OK;
+}
+
+int oo_peer_export(oo_ctx* c, void* handle64_host) {
+  if (!c || !handle64_host) return fail(OO_ERR_INVALID, "NULL argument");
+  CU_TRY(cudaSetDevice(c->device));
+  if (!c->peer_base) {
+    c->peer_stride = (c->M * c->N + 2) & ~1;
+    const size_t bytes = 256 + (size_t)2 * PEER_MAX * c->peer_stride * sizeof(double);
+    CU_TRY(cudaMalloc(&c->peer_base, bytes));
+    CU_TRY(cudaMemset(c->peer_base, 0, bytes));
+    CU_TRY(cudaMalloc((void**)&c->peer_err, sizeof(int)));
+    CU_TRY(cudaMemset(c->peer_err, 0, sizeof(int)));
+    CU_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, c->peer_base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64_host, &h, 64);
+  return OO_OK;
+}
+
+int oo_peer_attach(oo_ctx* c, const void* handles_host, int rank, int world) {
+  if (!c || !handles_host || rank < 0 || rank >= world)
+    return fail(OO_ERR_INVALID, "bad peer arguments");
+  if (world > PEER_MAX) return fail(OO_ERR_UNSUPPORTED, "at most %d peers", PEER_MAX);
+  if (!c->peer_base) return fail(OO_ERR_STATE, "call oo_peer_export first");
+  CU_TRY(cudaSetDevice(c->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      c->peer_map[r] = c->peer_base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles_host + 64 * r, 64);
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_map[r] = p;
+  }
+  c->rank = rank;
+  c->world = world;
+  c->peer_on = true;
+  return OO_OK;
+}
+
+int oo_peer_status(oo_ctx* c) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  if (!c->peer_on) return 0;
+  int err = 0;
+  CU_TRY(cudaMemcpy(&err, c->peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail(OO_ERR_NCCL, "fused all-reduce timed out waiting for a peer");
+  return 1;
 }
 
 int oo_allreduce(oo_ctx* c, double* buf_dev, size_t count) {

@@ -235,7 +235,27 @@ __global__ void __launch_bounds__(256) k_onebody(const OneBodyParams p) {
   }
 }
 
+// One-shot all-reduce over NVLink peer memory, fused into the last CTA of k_tail_row.
+// Every GPU owns a buffer  flags[2][world] | slots[2][world][stride]  that its peers map through
+// CUDA IPC.  Evaluation number `seq` (same on all ranks) uses parity seq&1:
+//   push   my (gradient | energy) vector into slot [parity][my_rank] of EVERY rank (remote stores)
+//   signal flags[parity][my_rank] = seq on every rank (after a system-scope fence)
+//   wait   until my own flags[parity][r] >= seq for all r
+//   sum    my slots[parity][0..world) in rank order -> identical bits on every rank.
+// A rank can be at most one evaluation ahead of the slowest one (it needs everybody's flag to
+// finish), so two parities suffice.
+constexpr int PEER_MAX = 8;
+struct PeerComm {
+  double* slots[PEER_MAX];               // rank r's slot area (peer-mapped)
+  unsigned long long* flags[PEER_MAX];   // rank r's flag area (peer-mapped)
+  int* error_flag;                       // set on wait time-out (never hang the GPU)
+  unsigned long long seq;
+  int rank, world, enabled;
+  int stride;                            // doubles per slot (>= M*N+1)
+};
+
 struct TailParams {
+  PeerComm comm;
   const double* T3;    // [nrows][Np^3]
   const double* Gp;    // [N][Np^3]
   const double* U;     // [M][N]
@@ -345,6 +365,39 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
     if (tid == 0) {
       p.out[(size_t)p.M * N] = v;
       *p.counter = 0u;
+    }
+    if (p.comm.enabled) {
+      // ---- fused one-shot all-reduce of out[0 .. M*N] over peer memory ----
+      __syncthreads();
+      const PeerComm& cm = p.comm;
+      const int len = p.M * N + 1, par = (int)(cm.seq & 1ull);
+      const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
+      for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+        const double val = __ldcg(p.out + idx);
+        for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < cm.world)
+        *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = cm.seq;
+      if (tid < cm.world) {
+        volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
+        const long long t_start = clock64();
+        while (*f < cm.seq) {
+          if (clock64() - t_start > 4000000000ll) {   // ~2 s: give up instead of hanging
+            *cm.error_flag = 1;
+            break;
+          }
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      const double* mine = cm.slots[cm.rank] + (size_t)par * cm.world * cm.stride;
+      for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+        double s = 0.0;
+        for (int r = 0; r < cm.world; ++r) s += __ldcg(mine + (size_t)r * cm.stride + idx);
+        p.out[idx] = s;
+      }
     }
   }
 }

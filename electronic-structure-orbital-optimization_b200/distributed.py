@@ -48,3 +48,24 @@ def attach_nccl(engine, group=None) -> None:
         buf.copy_(torch.tensor(list(uid), dtype=torch.uint8))
     dist.broadcast(buf, src=0, group=group)
     engine.attach_comm(bytes(buf.cpu().tolist()), rank, world)
+
+
+def attach_peer_memory(engine, group=None) -> None:
+    """Enable the all-reduce fused into the evaluation's last kernel: every rank exports the CUDA
+    IPC handle of its exchange buffer, torch.distributed all-gathers the 64-byte handles, every
+    rank maps its peers' buffers over NVLink.  All ranks must live on one node."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return
+    backend = dist.get_backend(group)
+    dev = engine.device if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(engine.peer_export()), dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    handles = b"".join(bytes(t.cpu().tolist()) for t in gathered)
+    engine.peer_attach(handles, rank, world)
+    dist.barrier(group)

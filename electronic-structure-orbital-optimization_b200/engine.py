@@ -172,6 +172,23 @@ class OrbitalEngine:
         _lib.check(self.lib.oo_comm_init(self._ctx, buf, rank, world))
         self.world = world
 
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this GPU's exchange buffer (fused all-reduce)."""
+        buf = (C.c_char * 64)()
+        _lib.check(self.lib.oo_peer_export(self._ctx, buf))
+        return bytes(buf)
+
+    def peer_attach(self, handles: bytes, rank: int, world: int) -> None:
+        buf = (C.c_char * (64 * world)).from_buffer_copy(handles)
+        _lib.check(self.lib.oo_peer_attach(self._ctx, buf, rank, world))
+        self.world = world
+
+    def peer_status(self) -> int:
+        rc = int(self.lib.oo_peer_status(self._ctx))
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
     @staticmethod
     def nccl_unique_id() -> bytes:
         buf = (C.c_char * 128)()
@@ -183,9 +200,9 @@ class OrbitalEngine:
         """(E 0-dim tensor, dE/dU [M,N]) on the device, asynchronous w.r.t. the host."""
         U = self._pad_u(_dev_f64(U, self.device))
         self._inputs_ready()
-        _lib.check(self.lib.oo_energy_grad(self._ctx, _ptr(U), _ptr(self._out)))
-        if allreduce and self.world > 1:
-            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(self._out), self.M * self.N + 1))
+        fn = self.lib.oo_energy_grad_allreduce if (allreduce and self.world > 1) \
+            else self.lib.oo_energy_grad
+        _lib.check(fn(self._ctx, _ptr(U), _ptr(self._out)))
         _lib.check(self.lib.oo_synchronize(self._ctx))
         MN = self.M * self.N
         grad = self._out[:MN].view(self.M, self.N)[:self.M_user].clone()
@@ -273,9 +290,9 @@ class OrbitalEngine:
 
     def enqueue_energy_grad(self, U_dev: torch.Tensor, allreduce: bool = True) -> None:
         """Asynchronous evaluation into the engine's output buffer (bench inner loop)."""
-        _lib.check(self.lib.oo_energy_grad(self._ctx, _ptr(U_dev), _ptr(self._out)))
-        if allreduce and self.world > 1:
-            _lib.check(self.lib.oo_allreduce(self._ctx, _ptr(self._out), self.M * self.N + 1))
+        fn = self.lib.oo_energy_grad_allreduce if (allreduce and self.world > 1) \
+            else self.lib.oo_energy_grad
+        _lib.check(fn(self._ctx, _ptr(U_dev), _ptr(self._out)))
 
     def synchronize(self) -> None:
         _lib.check(self.lib.oo_synchronize(self._ctx))

@@ -117,6 +117,11 @@ int oo_streamed_slabs(oo_ctx* ctx);
  * context stream.
  * Replaces base.py:534-582 (compute_rotated_energy) + pupo.py:85-103 (autograd gradient). */
 int oo_energy_grad(oo_ctx* ctx, const double* U_dev, double* out_dev);
+/* As oo_energy_grad, followed by the sum over all GPUs: through the one-shot all-reduce fused into
+ * the last kernel (NVLink peer memory, oo_peer_attach) when available, else through NCCL
+ * (oo_comm_init).  out_dev then holds E(U) and dE/dU on every rank, bit-identical across ranks in
+ * the fused mode (fixed rank-order summation). */
+int oo_energy_grad_allreduce(oo_ctx* ctx, const double* U_dev, double* out_dev);
 /* Same through host buffers: H2D of U, evaluation, all-reduce when a communicator is attached,
  * D2H of E and dE/dU, synchronous.  This is the reference-facing call used for end-to-end timing. */
 int oo_energy_grad_host(oo_ctx* ctx, const double* U_host, double* E_host, double* grad_host);
@@ -146,8 +151,18 @@ int oo_optimize(oo_ctx* ctx, double* U_io_host, double bb0, double tol, int maxi
 /* 128-byte NCCL unique id, to be created on rank 0 and broadcast by the host framework. */
 int oo_nccl_unique_id(void* id128_host);
 int oo_comm_init(oo_ctx* ctx, const void* id128_host, int rank, int world);
-/* In-place sum all-reduce of count doubles on the context stream (used for the M*N+1 buffer). */
+/* In-place NCCL sum all-reduce of count doubles on the context stream. */
 int oo_allreduce(oo_ctx* ctx, double* buf_dev, size_t count);
+/* Fused all-reduce over NVLink peer memory (one process per GPU, CUDA IPC).  oo_peer_export
+ * allocates this GPU's exchange buffer and returns its 64-byte cudaIpcMemHandle_t; the host
+ * framework all-gathers the handles; oo_peer_attach(handles[world][64]) maps the peers' buffers.
+ * From then on oo_energy_grad_allreduce / oo_energy_grad_host / oo_optimize do the all-reduce
+ * inside the evaluation's last kernel: the last CTA pushes the (M*N+1)-double vector into every
+ * peer, signals a flag, waits for the peers' flags and sums the contributions in rank order.
+ * oo_peer_status: 1 = attached and healthy, 0 = not attached, <0 = a wait timed out. */
+int oo_peer_export(oo_ctx* ctx, void* handle64_host);
+int oo_peer_attach(oo_ctx* ctx, const void* handles_host, int rank, int world);
+int oo_peer_status(oo_ctx* ctx);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Average device time (ms) of the kernels of the last oo_energy_grad call, measured with CUDA
