@@ -348,6 +348,16 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, 
   if ((rc = launch_qc(c, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
   CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));   // join
+  if (!c->pair_sym && c->mloc < c->M) {
+    // dense mode writes only the shard's rows; an in-place all-reduce of the previous evaluation
+    // may have left full rows elsewhere, so clear them
+    const size_t N = (size_t)c->N;
+    if (c->t0 > 0) CU_TRY(cudaMemsetAsync(out, 0, (size_t)c->t0 * N * sizeof(double), c->stream));
+    const size_t end = (size_t)(c->t0 + c->mloc);
+    if (end < (size_t)c->M)
+      CU_TRY(cudaMemsetAsync(out + end * N, 0, ((size_t)c->M - end) * N * sizeof(double),
+                             c->stream));
+  }
   const bool fused = reduce && c->peer_on && c->world > 1;
   if ((rc = launch_tail(c, U, out, done_flag, fused))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));

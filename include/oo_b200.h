@@ -103,7 +103,7 @@ int oo_set_rdms_spin(oo_ctx* ctx, const double* const* D_spin_dev, const double*
  * every pair {(t,q),(q,t)} is streamed from HBM (checkerboard choice: ~M/2 slabs per row, shards
  * stay balanced) and used for both rows.  With several GPUs every rank then contributes partial
  * gradient rows for ALL of U, completed by the same all-reduce.  enable=0 streams every slab of the
- * shard (dense mode: out_dev rows outside the shard are left untouched). */
+ * shard (dense mode: out_dev rows outside the shard are zero). */
 int oo_set_pair_symmetry(oo_ctx* ctx, int enable);
 /* Number of M x M slabs one evaluation streams from HBM on this GPU (algorithmic bytes =
  * 8*M*M*slabs). */
@@ -112,7 +112,7 @@ int oo_streamed_slabs(oo_ctx* ctx);
 /* ---- evaluation ---------------------------------------------------------------------------- */
 /* Enqueue one evaluation at U_dev [M][N].  out_dev [M*N+1] receives this GPU's partial dE/dU
  * (pair-symmetric mode: partial values for every row; dense mode: the shard's rows, other rows
- * left untouched, i.e. zero if the buffer was zeroed once) followed by the GPU's partial energy;
+ * are zeroed) followed by the GPU's partial energy;
  * the sum over GPUs is E(U), dE/dU.  With one GPU no reduction is needed.  Asynchronous on the
  * context stream.
  * Replaces base.py:534-582 (compute_rotated_energy) + pupo.py:85-103 (autograd gradient). */
