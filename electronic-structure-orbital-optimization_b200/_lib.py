@@ -18,7 +18,7 @@ SYMBOLS = [
     "oo_nccl_unique_id", "oo_comm_init", "oo_allreduce", "oo_set_timing", "oo_last_timing",
     "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
     "oo_ingest_spin_g", "oo_set_rdms_spin", "oo_energy_grad_allreduce", "oo_peer_export",
-    "oo_peer_attach", "oo_peer_status",
+    "oo_peer_attach", "oo_peer_status", "oo_set_integrals_generic",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -70,6 +70,7 @@ def load() -> C.CDLL:
     lib.oo_set_stream.argtypes = [vp, vp]
     lib.oo_synchronize.argtypes = [vp]
     lib.oo_set_integrals.argtypes = [vp, vp, vp, C.c_uint]
+    lib.oo_set_integrals_generic.argtypes = [vp, vp, vp, vp]
     lib.oo_check_v4_symmetry.argtypes = [C.c_int, vp, C.c_int, dp]
     lib.oo_set_rdms.argtypes = [vp, vp, vp]
     lib.oo_energy_grad.argtypes = [vp, vp, vp]

@@ -108,6 +108,10 @@ struct oo_ctx {
   bool own_stream = false;
   const double* h = nullptr;
   const double* g = nullptr;
+  const double* g2 = nullptr;          // generic mode: pair-transposed tensor g2[r,s,p,q] = g[p,q,r,s]
+  bool generic = false;                // no V4 symmetry: two dense passes, four gradient slots
+  alignas(64) CUtensorMap tmap2;
+  double* Gp_slot[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned gflags = 0;
   bool have_ints = false, have_rdms = false;
   alignas(64) CUtensorMap tmap;
@@ -169,7 +173,7 @@ int get_encode_fn(encode_tiled_t* fn) {
 }
 
 // 3-D view of the shard: (s: M, r: M, slab: mloc*M), box 16 x 256 x 1, 128B swizzle, zero fill.
-int build_tmap(oo_ctx* c) {
+int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map) {
   encode_tiled_t enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
@@ -177,7 +181,7 @@ int build_tmap(oo_ctx* c) {
   const cuuint64_t strides[2] = {(cuuint64_t)c->M * 8, (cuuint64_t)c->M * c->M * 8};
   const cuuint32_t box[3] = {K1_KC, K1_ROWS, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(c->g), dims,
+  CUresult r = enc(out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OO_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -185,17 +189,18 @@ int build_tmap(oo_ctx* c) {
 }
 
 template <int NT>
-int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag) {
+int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor) {
   K1Params p;
   p.U = U;
   p.Y = c->Y;
-  p.YT = c->pair_sym ? c->YT : nullptr;
+  const bool pair = c->pair_sym && !c->generic;
+  p.YT = pair ? c->YT : nullptr;
   p.Upad = c->Upad;
   p.done_flag = done_flag;
   p.M = c->M;
   p.N = c->N;
-  p.slab_coord = c->pair_sym ? c->slab_coord : nullptr;
-  p.nslab = c->pair_sym ? c->nsel : c->mloc * c->M;
+  p.slab_coord = pair ? c->slab_coord : nullptr;
+  p.nslab = pair ? c->nsel : c->mloc * c->M;
   p.nstage = c->nstage;
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
@@ -206,24 +211,25 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag) {
     attr_set[c->device & 7] = true;
   }
   const int grid = std::min(c->num_sms, p.nslab);
-  k1_half_transform<NT><<<grid, K1_THREADS, c->k1_smem, c->stream>>>(c->tmap, p);
+  k1_half_transform<NT><<<grid, K1_THREADS, c->k1_smem, c->stream>>>(
+      second_tensor ? c->tmap2 : c->tmap, p);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
 }
 
-int launch_k1(oo_ctx* c, const double* U, const int* done_flag) {
+int launch_k1(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor = false) {
   switch (c->NT) {
-    case 1: return launch_k1_t<1>(c, U, done_flag);
-    case 2: return launch_k1_t<2>(c, U, done_flag);
-    case 3: return launch_k1_t<3>(c, U, done_flag);
-    case 4: return launch_k1_t<4>(c, U, done_flag);
+    case 1: return launch_k1_t<1>(c, U, done_flag, second_tensor);
+    case 2: return launch_k1_t<2>(c, U, done_flag, second_tensor);
+    case 3: return launch_k1_t<3>(c, U, done_flag, second_tensor);
+    case 4: return launch_k1_t<4>(c, U, done_flag, second_tensor);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
 
 template <int NT>
-int launch_qc_t(oo_ctx* c, const int* done_flag) {
+int launch_qc_t(oo_ctx* c, const int* done_flag, bool dense_mirror) {
   constexpr int Np = NT * 8;
   const size_t smem = qc_smem_bytes(NT, c->M, c->mloc);
   if (smem > 200 * 1024) return fail(OO_ERR_UNSUPPORTED, "M too large for k_qcontract smem");
@@ -240,13 +246,15 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
   qp.YT = c->YT;
   qp.Upad = c->Upad;
   qp.T3 = c->T3;
-  qp.rowstart = c->pair_sym ? c->rowstart : nullptr;
+  const bool pair = c->pair_sym && !c->generic;
+  qp.rowstart = pair ? c->rowstart : nullptr;
+  qp.dense_mirror = dense_mirror ? 1 : 0;
   qp.done_flag = done_flag;
   qp.M = c->M;
   qp.t0 = c->t0;
   qp.mloc = c->mloc;
-  qp.row0 = c->pair_sym ? 0 : c->t0;
-  qp.nrows = c->pair_sym ? c->M : c->mloc;
+  qp.row0 = pair ? 0 : c->t0;
+  qp.nrows = pair ? c->M : c->mloc;
   dim3 grid(qp.nrows, (Np * Np + QC_ECHUNK - 1) / QC_ECHUNK);
   k_qcontract<NT><<<grid, QC_THREADS, smem, c->stream>>>(qp);
   CU_TRY(cudaGetLastError());
@@ -255,7 +263,8 @@ int launch_qc_t(oo_ctx* c, const int* done_flag) {
 }
 
 template <int NT>
-int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused) {
+int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
+                  int slot) {
   TailParams tp;
   memset(&tp.comm, 0, sizeof tp.comm);
   if (fused) {
@@ -271,7 +280,7 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
     }
   }
   tp.T3 = c->T3;
-  tp.Gp = c->Gp;
+  tp.Gp = slot < 0 ? c->Gp : c->Gp_slot[slot];
   tp.U = U;
   tp.B1 = c->B1;
   tp.B12 = c->B12;
@@ -283,9 +292,11 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.N = c->N;
   tp.t0 = c->t0;
   tp.mloc = c->mloc;
-  tp.row0 = c->pair_sym ? 0 : c->t0;
-  tp.nrows = c->pair_sym ? c->M : c->mloc;
-  tp.two_body_grad_factor = 4.0;
+  const bool pair = c->pair_sym && !c->generic;
+  tp.row0 = pair ? 0 : c->t0;
+  tp.nrows = pair ? c->M : c->mloc;
+  tp.two_body_grad_factor = slot < 0 ? 4.0 : 1.0;
+  tp.accumulate = slot > 0 ? 1 : 0;
   constexpr int R = tail_rows(NT);
   k_tail_row<NT><<<(tp.nrows + R - 1) / R, TAIL_THREADS, 0, c->stream>>>(tp);
   CU_TRY(cudaGetLastError());
@@ -293,22 +304,23 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   return OO_OK;
 }
 
-int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused) {
+int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
+                int slot = -1) {
   switch (c->NT) {
-    case 1: return launch_tail_t<1>(c, U, out, done_flag, fused);
-    case 2: return launch_tail_t<2>(c, U, out, done_flag, fused);
-    case 3: return launch_tail_t<3>(c, U, out, done_flag, fused);
-    case 4: return launch_tail_t<4>(c, U, out, done_flag, fused);
+    case 1: return launch_tail_t<1>(c, U, out, done_flag, fused, slot);
+    case 2: return launch_tail_t<2>(c, U, out, done_flag, fused, slot);
+    case 3: return launch_tail_t<3>(c, U, out, done_flag, fused, slot);
+    case 4: return launch_tail_t<4>(c, U, out, done_flag, fused, slot);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
 
-int launch_qc(oo_ctx* c, const int* done_flag) {
+int launch_qc(oo_ctx* c, const int* done_flag, bool dense_mirror = false) {
   switch (c->NT) {
-    case 1: return launch_qc_t<1>(c, done_flag);
-    case 2: return launch_qc_t<2>(c, done_flag);
-    case 3: return launch_qc_t<3>(c, done_flag);
-    case 4: return launch_qc_t<4>(c, done_flag);
+    case 1: return launch_qc_t<1>(c, done_flag, dense_mirror);
+    case 2: return launch_qc_t<2>(c, done_flag, dense_mirror);
+    case 3: return launch_qc_t<3>(c, done_flag, dense_mirror);
+    case 4: return launch_qc_t<4>(c, done_flag, dense_mirror);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -342,13 +354,35 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, 
     c->launches++;
   }
   CU_TRY(cudaEventRecord(c->ev_join, c->aux));
+  if (c->generic) {
+    // no V4 symmetry: one slot term per index position.  Slots 0,1 come from
+    // the half transform of g, slots 2,3 from the half transform of the pair-transposed tensor.
+    if (c->world > 1 || c->mloc != c->M)
+      return fail(OO_ERR_UNSUPPORTED, "the generic (non-symmetric) path is single-GPU only");
+    if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = launch_k1(c, U, done_flag, false))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = launch_qc(c, done_flag, false))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    if ((rc = launch_tail(c, U, out, done_flag, false, 0))) return rc;
+    if ((rc = launch_qc(c, done_flag, true))) return rc;
+    if ((rc = launch_tail(c, U, out, done_flag, false, 1))) return rc;
+    if ((rc = launch_k1(c, U, done_flag, true))) return rc;
+    if ((rc = launch_qc(c, done_flag, false))) return rc;
+    if ((rc = launch_tail(c, U, out, done_flag, false, 2))) return rc;
+    if ((rc = launch_qc(c, done_flag, true))) return rc;
+    if ((rc = launch_tail(c, U, out, done_flag, false, 3))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
+    return OO_OK;
+  }
   if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_k1(c, U, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
   if ((rc = launch_qc(c, done_flag))) return rc;
   if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
   CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));   // join
-  if (!c->pair_sym && c->mloc < c->M) {
+  if ((!c->pair_sym || c->generic) && c->mloc < c->M) {
     // dense mode writes only the shard's rows; an in-place all-reduce of the previous evaluation
     // may have left full rows elsewhere, so clear them
     const size_t N = (size_t)c->N;
@@ -513,6 +547,8 @@ int oo_destroy(oo_ctx* c) {
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   for (int r = 0; r < PEER_MAX; ++r)
     if (c->peer_map[r] && c->peer_map[r] != c->peer_base) cudaIpcCloseMemHandle(c->peer_map[r]);
+  for (int s2 = 0; s2 < 4; ++s2)
+    if (c->Gp_slot[s2]) cudaFree(c->Gp_slot[s2]);
   if (c->peer_base) cudaFree(c->peer_base);
   if (c->peer_err) cudaFree(c->peer_err);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
@@ -569,15 +605,43 @@ int oo_set_integrals(oo_ctx* c, const double* h_dev, const double* g_dev, unsign
   if (((uintptr_t)g_dev & 15) != 0) return fail(OO_ERR_INVALID, "g must be 16-byte aligned");
   if (!(flags & OO_G_V4_SYMMETRIC))
     return fail(OO_ERR_UNSUPPORTED,
-                "only V4-symmetric two-body tensors (g[pqrs]=g[qpsr]=g[rspq]) are supported; "
-                "verify with oo_check_v4_symmetry and pass OO_G_V4_SYMMETRIC");
+                "two-body tensors without V4 symmetry (g[pqrs]=g[qpsr]=g[rspq]) need the "
+                "pair-transposed copy as well: use oo_set_integrals_generic");
   CU_TRY(cudaSetDevice(c->device));
   c->h = h_dev;
   c->g = g_dev;
   c->gflags = flags;
-  int rc = build_tmap(c);
+  int rc = build_tmap(c, c->g, &c->tmap);
   if (rc) return rc;
+  c->generic = false;
   c->have_ints = true;
+  return OO_OK;
+}
+
+int oo_set_integrals_generic(oo_ctx* c, const double* h_dev, const double* g_dev,
+                             const double* g_pair_transposed_dev) {
+  if (!c || !h_dev || !g_dev || !g_pair_transposed_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  if ((((uintptr_t)g_dev) | ((uintptr_t)g_pair_transposed_dev)) & 15)
+    return fail(OO_ERR_INVALID, "g must be 16-byte aligned");
+  if (c->mloc != c->M) return fail(OO_ERR_UNSUPPORTED, "the generic path is single-GPU only");
+  CU_TRY(cudaSetDevice(c->device));
+  c->h = h_dev;
+  c->g = g_dev;
+  c->g2 = g_pair_transposed_dev;
+  c->gflags = 0;
+  int rc = build_tmap(c, c->g, &c->tmap);
+  if (rc) return rc;
+  if ((rc = build_tmap(c, c->g2, &c->tmap2))) return rc;
+  if (!c->Gp_slot[0]) {
+    const size_t n = (size_t)c->N * c->Np * c->Np * c->Np;
+    for (int s = 0; s < 4; ++s) {
+      CU_TRY(cudaMalloc((void**)&c->Gp_slot[s], n * sizeof(double)));
+      CU_TRY(cudaMemset(c->Gp_slot[s], 0, n * sizeof(double)));
+    }
+  }
+  c->generic = true;
+  c->have_ints = true;
+  c->have_rdms = false;   // the 2-RDM must be re-ingested in the four slot layouts
   return OO_OK;
 }
 
@@ -605,6 +669,12 @@ int oo_set_rdms(oo_ctx* c, const double* D_dev, const double* G_dev) {
   k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp, c->N, c->Np, 1);
   CU_TRY(cudaGetLastError());
   c->launches++;
+  if (c->generic)
+    for (int s = 0; s < 4; ++s) {
+      k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp_slot[s], c->N, c->Np, 0, s);
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+    }
   c->have_rdms = true;
   return OO_OK;
 }
@@ -680,6 +750,13 @@ int oo_set_rdms_spin(oo_ctx* c, const double* const* D_spin_dev, const double* c
   CU_TRY(cudaGetLastError());
   k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(c->Gtmp, c->Gp, c->N, c->Np, 1);
   CU_TRY(cudaGetLastError());
+  if (c->generic)
+    for (int s = 0; s < 4; ++s) {
+      k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(c->Gtmp, c->Gp_slot[s], c->N, c->Np, 0,
+                                                         s);
+      CU_TRY(cudaGetLastError());
+      c->launches++;
+    }
   c->launches += 2;
   c->have_rdms = true;
   return OO_OK;
@@ -722,8 +799,8 @@ int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_ro
     if ((rc = launch_k1(c, U_dev, nullptr))) return rc;
     if ((rc = launch_qc(c, nullptr))) return rc;
     k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np,
-                                                   c->pair_sym ? 0 : c->t0,
-                                                   c->pair_sym ? c->M : c->mloc);
+                                                   (c->pair_sym && !c->generic) ? 0 : c->t0,
+                                                   (c->pair_sym && !c->generic) ? c->M : c->mloc);
     CU_TRY(cudaGetLastError());
     c->launches++;
   }
@@ -967,6 +1044,7 @@ int oo_set_pair_symmetry(oo_ctx* c, int enable) {
 
 int oo_streamed_slabs(oo_ctx* c) {
   if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  if (c->generic) return 2 * c->mloc * c->M;
   return c->pair_sym ? c->nsel : c->mloc * c->M;
 }
 

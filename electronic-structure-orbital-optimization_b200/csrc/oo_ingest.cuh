@@ -36,8 +36,12 @@ __global__ void k_v4_symmetry(const double* __restrict__ g, int M, unsigned long
 
 // Gp[a][j][l*Np+k] = (1/4)(G[a,j,k,l] + G[j,a,l,k] + G[k,l,a,j] + G[l,k,j,a])  (V4 average),
 // zero in the padding (j, k or l >= N).  grid N*Np, block Np*Np threads (looped).
+// symmetrise = 0 selects one of the four slot layouts of the generic (no symmetry) gradient:
+//   slot 0: Gp[a][j][l*Np+k] = G[a,j,k,l]      slot 1: Gp[a][i][l*Np+k] = G[i,a,k,l]
+//   slot 2: Gp[a][l][j*Np+i] = G[i,j,a,l]      slot 3: Gp[a][k][j*Np+i] = G[i,j,k,a]
+// (middle index = the plane index of T3, tile index = (row, col) of the K1 tile as stored).
 __global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict__ Gp, int N, int Np,
-                                int symmetrise) {
+                                int symmetrise, int slot = 0) {
   const int a = blockIdx.x / Np, j = blockIdx.x % Np;
   const int Np2 = Np * Np;
   const size_t N2 = (size_t)N * N, N3 = N2 * N;
@@ -45,7 +49,10 @@ __global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict
     const int l = e / Np, k = e - l * Np;
     double v = 0.0;
     if (j < N && k < N && l < N) {
-      v = G[a * N3 + j * N2 + (size_t)k * N + l];
+      if (!symmetrise && slot == 1) v = G[j * N3 + a * N2 + (size_t)k * N + l];
+      else if (!symmetrise && slot == 2) v = G[k * N3 + l * N2 + (size_t)a * N + j];
+      else if (!symmetrise && slot == 3) v = G[k * N3 + l * N2 + (size_t)j * N + a];
+      else v = G[a * N3 + j * N2 + (size_t)k * N + l];
       if (symmetrise) {
         v += G[j * N3 + a * N2 + (size_t)l * N + k];
         v += G[k * N3 + l * N2 + (size_t)a * N + j];

@@ -57,6 +57,8 @@ struct QCParams {
   const double* Upad;    // [M][Np] zero-padded U (written by K1's CTA 0)
   double* T3;            // [nrows][Np][Np*Np]
   const int* rowstart;   // pair-symmetric mode: [mloc] first slab index of each row; NULL = dense
+  int dense_mirror;      // dense mode only: row x takes the tiles (p,x) for all p of the shard
+                         // (partner p, not transposed) instead of its own tiles (x,q)
   const int* done_flag;
   int M, t0, mloc;
   int row0, nrows;       // rows x produced: dense [t0, t0+mloc); pair-symmetric [0, M)
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(QC_THREADS, NT <= 2 ? 2 : 1) k_qcontract(const
     const int hi_beg = max(x + 1, p.t0);                 // t in [hi_beg, t1), parity (x+1)&1
     hi_first = hi_beg + ((((x + 1) & 1) - (hi_beg & 1)) & 1);
     n_hi = t1 > hi_first ? (t1 - hi_first + 1) >> 1 : 0;
+  } else if (p.dense_mirror) {
+    n_own = p.mloc;                                      // tiles (t0+i, x)
   } else if (mine) {
     n_own = M;
   }
@@ -108,6 +112,9 @@ __global__ void __launch_bounds__(QC_THREADS, NT <= 2 ? 2 : 1) k_qcontract(const
       if (p.rowstart) {
         tile = __ldg(p.rowstart + (x - p.t0)) + i;
         urow = pair_ith_q(x, i);
+      } else if (p.dense_mirror) {
+        tile = i * M + x;
+        urow = p.t0 + i;
       } else {
         tile = (x - p.t0) * M + i;
         urow = i;
@@ -267,7 +274,8 @@ struct TailParams {
   const int* done_flag;
   int M, N, t0, mloc;  // shard: the one-body terms are added for rows in [t0, t0+mloc) only
   int row0, nrows;
-  double two_body_grad_factor;  // 4 for the one-pass (V4-symmetric) gradient
+  double two_body_grad_factor;  // 4 for the one-pass (V4-symmetric) gradient, 1 per generic slot
+  int accumulate;               // generic slots 1..3: out[x] += A[x], energy untouched
 };
 
 constexpr int TAIL_THREADS = 256;
@@ -338,7 +346,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
         b1 = p.B1[(size_t)(x - p.t0) * N + a];
         b12 = p.B12[(size_t)(x - p.t0) * N + a];
       }
-      p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
+      if (p.accumulate) p.out[(size_t)x * N + a] += p.two_body_grad_factor * av;
+      else p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
       ev = __ldg(p.U + (size_t)x * N + a) * (av + b1);
     }
     s_e[r][a] = ev;
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
     for (int i = tid; i < p.nrows; i += TAIL_THREADS) v += ((volatile double*)p.rowE)[i];
     v = block_sum(v, scratch);                  // fixed tree: deterministic
     if (tid == 0) {
-      p.out[(size_t)p.M * N] = v;
+      if (!p.accumulate) p.out[(size_t)p.M * N] = v;
       *p.counter = 0u;
     }
     if (p.comm.enabled) {

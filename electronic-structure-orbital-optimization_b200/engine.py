@@ -99,7 +99,7 @@ class OrbitalEngine:
         return float(out[0]), float(out[1])
 
     def set_integrals(self, h: torch.Tensor, g: torch.Tensor, assume_v4_symmetric: bool = False,
-                      sym_rtol: float = 1e-11) -> None:
+                      sym_rtol: float = 1e-11, allow_generic: bool = True) -> None:
         """h [M,M]; g [mloc,M,M,M] (this shard's rows).  The tensors are used in place (no copy)
         when already on the device, contiguous and M is even."""
         if tuple(h.shape) != (self.M_user, self.M_user):
@@ -109,16 +109,27 @@ class OrbitalEngine:
                              f"{self.M_user}], got {tuple(g.shape)}")
         h = self._pad_h(_dev_f64(h, self.device))
         g = self._pad_g(_dev_f64(g, self.device))
+        self.generic = False
         if not assume_v4_symmetric:
             if self.mloc != self.M:
                 raise ValueError("a sharded g cannot be verified locally; verify the full tensor "
                                  "before sharding and pass assume_v4_symmetric=True")
             asym, gmax = self.check_v4_symmetry(g)
             if asym > sym_rtol * max(gmax, 1e-300):
-                raise NotImplementedError(
-                    f"two-body integrals are not V4-symmetric (max asymmetry {asym:.3e}, "
-                    f"max |g| {gmax:.3e}); the one-pass gradient needs g[pqrs]=g[qpsr]=g[rspq]")
+                if not allow_generic:
+                    raise NotImplementedError(
+                        f"two-body integrals are not V4-symmetric (max asymmetry {asym:.3e}, "
+                        f"max |g| {gmax:.3e}); the one-pass gradient needs g[pqrs]=g[qpsr]=g[rspq]")
+                # generic path: second dense pass over the pair-transposed tensor (2x memory)
+                g_pt = g.permute(2, 3, 0, 1).contiguous()
+                self._keep["h"], self._keep["g"], self._keep["g_pt"] = h, g, g_pt
+                self._inputs_ready()
+                _lib.check(self.lib.oo_set_integrals_generic(self._ctx, _ptr(h), _ptr(g),
+                                                             _ptr(g_pt)))
+                self.generic = True
+                return
         self._keep["h"], self._keep["g"] = h, g
+        self._keep.pop("g_pt", None)
         self._inputs_ready()
         _lib.check(self.lib.oo_set_integrals(self._ctx, _ptr(h), _ptr(g), _lib.OO_G_V4_SYMMETRIC))
 

@@ -74,6 +74,13 @@ int oo_synchronize(oo_ctx* ctx);
  * strides are multiples of 16 bytes).  Replaces the .to(device) shuttling of the integral tensors,
  * opt_orb_minimum_eigensolver.py:219-222. */
 int oo_set_integrals(oo_ctx* ctx, const double* h_dev, const double* g_dev, unsigned flags);
+/* Two-body tensors WITHOUT V4 symmetry (single GPU only): registers g_dev [M]^4 and its
+ * pair-transposed copy g_pt_dev[r][s][p][q] = g[p][q][r][s].  Every evaluation then makes two dense
+ * passes (one per tensor) and builds dE/dU from the four index-slot terms, with the 2-RDM used as
+ * given (no symmetrisation).  Four times the work of the symmetric path; completes the contract
+ * of compute_rotated_energy for arbitrary real tensors (base.py:534-563, pupo.py:85-103). */
+int oo_set_integrals_generic(oo_ctx* ctx, const double* h_dev, const double* g_dev,
+                             const double* g_pt_dev);
 /* Max |g - g∘pi| over the three V4 permutations and max |g| of a FULL (unsharded) device tensor
  * g_dev[M][M][M][M]; out_host[0]=max asymmetry, out_host[1]=max |g|. */
 int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_host);
