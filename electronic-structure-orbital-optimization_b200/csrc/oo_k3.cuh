@@ -17,7 +17,7 @@
 
 namespace oo {
 
-constexpr int K3_THREADS = 256;
+constexpr int K3_THREADS = 1024;  // one CTA, latency-bound: short per-thread loops
 constexpr int K3_NMAX = 32;
 
 struct OptState {
@@ -189,31 +189,47 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
 }
 
 // U_out = orth(V) = V (V^T V)^(-1/2) for an M x N matrix V in global memory.  One CTA.  V and
-// U_out may alias.  smem: sA, sB1, sB2, sB3 are K3_NMAX*(K3_NMAX+1) doubles each; cs 4*K3_NMAX;
+// U_out must be distinct buffers.  smem: sA, sB1, sB2, sB3 are K3_NMAX*(K3_NMAX+1) doubles each; cs 4*K3_NMAX;
 // scratch 32 doubles.
 __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
                                    double* sB1, double* sB2, double* sB3, double* cs,
                                    double* scratch, int* sflag) {
   constexpr int LD = K3_NMAX + 1;
   const int tid = threadIdx.x, nth = blockDim.x;
-  // Gram matrix V^T V (upper triangle computed, mirrored)
-  for (int idx = tid; idx < N * N; idx += nth) {
-    const int i = idx / N, j = idx - i * N;
-    if (j >= i) {
+  // Gram matrix V^T V: the t-range is split over nth / N^2 thread groups, partials summed in
+  // fixed order through shared memory (sB3 is free until the Newton-Schulz iteration starts)
+  {
+    const int nn = N * N;
+    const int tsplit = max(1, min(nth / nn, (K3_NMAX * (K3_NMAX + 1)) / nn));
+    const int chunk = (M + tsplit - 1) / tsplit;
+    for (int idx = tid; idx < nn * tsplit; idx += nth) {
+      const int e = idx % nn, part = idx / nn;
+      const int i = e / N, j = e - i * N;
+      const int tb = part * chunk, te = min(M, tb + chunk);
       double s0 = 0.0, s1 = 0.0;
-      int t = 0;
+      int t = tb;
 #pragma unroll 4
-      for (; t + 1 < M; t += 2) {
+      for (; t + 1 < te; t += 2) {
         s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
         s1 = fma(V[(size_t)(t + 1) * N + i], V[(size_t)(t + 1) * N + j], s1);
       }
-      if (t < M) s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
-      const double s = s0 + s1;
-      sA[i * LD + j] = s;
-      sA[j * LD + i] = s;
+      if (t < te) s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
+      sB3[part * nn + e] = s0 + s1;
     }
+    __syncthreads();
+    for (int e = tid; e < nn; e += nth) {
+      double s = 0.0;
+      for (int part = 0; part < tsplit; ++part) s += sB3[part * nn + e];
+      sA[(e / N) * LD + (e % N)] = s;
+    }
+    __syncthreads();
+    // exact symmetry (the two triangles were summed in different orders)
+    for (int e = tid; e < nn; e += nth) {
+      const int i = e / N, j = e - i * N;
+      if (j > i) sA[j * LD + i] = sA[i * LD + j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   double scale = 1.0;
   double* S = sB2;  // inverse square root (up to `scale`) ends up here
   const bool ok = newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale);
@@ -237,14 +253,18 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
     scale = 1.0;
     __syncthreads();
   }
-  // U = V S ; row-wise so V and Uout may alias (each thread owns whole rows)
-  for (int t = tid; t < M; t += nth) {
-    double v[K3_NMAX];
-    for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j] * scale;
-    for (int j = 0; j < N; ++j) {
-      double s = 0.0;
-      for (int m = 0; m < N; ++m) s = fma(v[m], S[m * LD + j], s);
-      Uout[(size_t)t * N + j] = s;
+  // U = V S  (V and Uout must not alias): nth / M threads share a row, each a subset of columns
+  {
+    const int per_row = max(1, nth / M);
+    for (int idx = tid; idx < M * per_row; idx += nth) {
+      const int t = idx / per_row, grp = idx - t * per_row;
+      double v[K3_NMAX];
+      for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j] * scale;
+      for (int j = grp; j < N; j += per_row) {
+        double s = 0.0;
+        for (int m = 0; m < N; ++m) s = fma(v[m], S[m * LD + j], s);
+        Uout[(size_t)t * N + j] = s;
+      }
     }
   }
   __syncthreads();
