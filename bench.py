@@ -333,6 +333,9 @@ def main():
                     "d2h_bytes_per_step": (M * N + 1) * 8,
                     "api": "OrbitalEngine.energy_grad_host -> oo_energy_grad_host (host buffers)"},
             "inner_loop": {"iterations_per_s": inner_rate, "iterations": inner_iters,
+                           "newton_schulz_iterations_per_retraction":
+                               res["newton_schulz_iterations"] / max(1, inner_iters),
+                           "jacobi_fallbacks": res["jacobi_fallbacks"],
                            "what": "oo_optimize: device-resident loop of pupo.py:161-350, one "
                                    "evaluation + retraction + BB step + stop test per iteration, "
                                    "host round trip only every 4 iterations (flag poll)"},

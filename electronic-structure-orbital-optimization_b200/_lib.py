@@ -19,6 +19,7 @@ SYMBOLS = [
     "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
     "oo_ingest_spin_g", "oo_set_rdms_spin", "oo_energy_grad_allreduce", "oo_peer_export",
     "oo_peer_attach", "oo_peer_status", "oo_set_integrals_generic",
+    "oo_retraction_stats",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -92,6 +93,7 @@ def load() -> C.CDLL:
     lib.oo_launch_count.argtypes = [vp]
     lib.oo_launch_count.restype = C.c_longlong
     lib.oo_measure_peaks.argtypes = [C.c_int, sz, dp]
+    lib.oo_retraction_stats.argtypes = [vp, ip, ip]
     lib.oo_set_pair_symmetry.argtypes = [vp, C.c_int]
     lib.oo_streamed_slabs.argtypes = [vp]
     lib.oo_ingest_spin_g.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.POINTER(C.c_uint), dp]

@@ -149,6 +149,7 @@ struct oo_ctx {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[5] = {0, 0, 0, 0, 0};
   long long launches = 0;
+  int last_ns_iters = 0, last_jacobi_calls = 0;   // telemetry of the last oo_optimize
 };
 
 namespace {
@@ -942,6 +943,8 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   if (n_iter) *n_iter = fin.k_final;
   if (E_final) *E_final = fin.E_final;
   if (bb_final) *bb_final = fin.alpha;
+  c->last_ns_iters = fin.ns_iters;
+  c->last_jacobi_calls = fin.jacobi_calls;
   if (fin.nan_flag) return fail(OO_ERR_NUMERIC, "non-finite value met during the optimisation");
   return OO_OK;
 }
@@ -1065,6 +1068,13 @@ int oo_last_timing(oo_ctx* c, float* ms5_host) {
 }
 
 long long oo_launch_count(oo_ctx* c) { return c ? c->launches : 0; }
+
+int oo_retraction_stats(oo_ctx* c, int* newton_schulz_iterations, int* jacobi_fallbacks) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  if (newton_schulz_iterations) *newton_schulz_iterations = c->last_ns_iters;
+  if (jacobi_fallbacks) *jacobi_fallbacks = c->last_jacobi_calls;
+  return OO_OK;
+}
 
 int oo_measure_peaks(int device, size_t bytes, double* out_host) {
   if (!out_host) return fail(OO_ERR_INVALID, "NULL argument");

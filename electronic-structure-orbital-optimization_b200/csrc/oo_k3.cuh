@@ -32,6 +32,8 @@ struct OptState {
   int done;          // stop flag (kernels become no-ops when set)
   int k_final;       // iteration_number at loop exit
   int nan_flag;      // set when a non-finite value is met
+  int ns_iters;      // telemetry: Newton-Schulz iterations summed over all retractions
+  int jacobi_calls;  // telemetry: retractions that fell back to the Jacobi eigensolver
   int pad;
 };
 
@@ -120,7 +122,8 @@ __device__ inline void jacobi_eigh_smem(double* A, double* Q, double* cs, int n,
 // eigensolver needs ~100 us.  Returns false if 60 iterations did not reach ||I - T||_F < 1e-8
 // (then the caller falls back to the eigensolver).  All threads of the CTA must call.
 __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double* Z, double* W,
-                                             int n, double* scratch, double* inv_sqrt_c) {
+                                             int n, double* scratch, double* inv_sqrt_c,
+                                             int* iters_out) {
   constexpr int LD = K3_NMAX + 1;
   constexpr int EPT = (K3_NMAX * K3_NMAX + K3_THREADS - 1) / K3_THREADS;  // elements per thread
   const int tid = threadIdx.x, nth = blockDim.x, nn = n * n;
@@ -179,6 +182,7 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
       }
     }
     __syncthreads();
+    if (iters_out) *iters_out = it + 1;
     if (r < 1e-16) {  // ||I - T||_F < 1e-8 before this update => ~1e-16 after it
       converged = true;
       break;
@@ -193,7 +197,7 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
 // scratch 32 doubles.
 __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
                                    double* sB1, double* sB2, double* sB3, double* cs,
-                                   double* scratch, int* sflag) {
+                                   double* scratch, int* sflag, int* telemetry = nullptr) {
   constexpr int LD = K3_NMAX + 1;
   const int tid = threadIdx.x, nth = blockDim.x;
   // Gram matrix V^T V: the t-range is split over nth / N^2 thread groups, partials summed in
@@ -232,7 +236,12 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
   }
   double scale = 1.0;
   double* S = sB2;  // inverse square root (up to `scale`) ends up here
-  const bool ok = newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale);
+  int ns_it = 0;
+  const bool ok = newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale, &ns_it);
+  if (telemetry && tid == 0) {
+    telemetry[0] += ns_it;
+    if (!ok) telemetry[1] += 1;
+  }
   if (!ok) {
     // robust path: S = Q diag(w^-1/2) Q^T from the Jacobi eigen-decomposition (reference:
     // torch.linalg.eigh, partial_unitary_projection_optimizer.py:80-81)
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
     p.Gprev[i] = g;
   }
   __syncthreads();
-  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
+  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, &st->ns_iters);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;

@@ -277,8 +277,11 @@ class OrbitalEngine:
                                         float(tol), int(maxiter), float(decay),
                                         hist.ctypes.data_as(C.c_void_p), cap, C.byref(n_iter),
                                         C.byref(E), C.byref(bb)))
+        ns, jac = C.c_int(), C.c_int()
+        _lib.check(self.lib.oo_retraction_stats(self._ctx, C.byref(ns), C.byref(jac)))
         return {"U": Uh[:self.M_user].copy(), "energy": float(E.value), "n_iter": int(n_iter.value),
-                "E_hist": hist, "stepsize": float(bb.value)}
+                "E_hist": hist, "stepsize": float(bb.value),
+                "newton_schulz_iterations": int(ns.value), "jacobi_fallbacks": int(jac.value)}
 
     # -- measurement ---------------------------------------------------------------------------
     def use_stream(self, stream: Optional["torch.cuda.Stream"]) -> None:

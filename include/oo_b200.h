@@ -180,6 +180,9 @@ int oo_set_timing(oo_ctx* ctx, int enable);
 int oo_last_timing(oo_ctx* ctx, float* ms5_host);
 /* Number of kernels launched by this context since creation. */
 long long oo_launch_count(oo_ctx* ctx);
+/* Telemetry of the last oo_optimize: Newton-Schulz iterations summed over all retractions and the
+ * number of retractions that fell back to the Jacobi eigensolver. */
+int oo_retraction_stats(oo_ctx* ctx, int* newton_schulz_iterations, int* jacobi_fallbacks);
 /* Measured FP64 peaks of the device: out_host[0] = DMMA.8x8x4 TFLOP/s (register-resident loop),
  * out_host[1] = DFMA TFLOP/s, out_host[2] = streaming read GB/s (LDG.128 sum over `bytes`). */
 int oo_measure_peaks(int device, size_t bytes, double* out_host);
