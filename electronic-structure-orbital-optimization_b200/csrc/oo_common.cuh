@@ -88,8 +88,8 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   return x;
 }
 
-// Deterministic block-wide sum (fixed tree). blockDim.x must be a multiple of 32, <= 1024.
-// `scratch` needs 32 doubles of shared memory. Result is valid in every thread.
+// Deterministic block-wide sum (fixed shuffle tree in both stages).  blockDim.x must be a multiple
+// of 32, <= 1024.  `scratch` needs 33 doubles of shared memory.  Result is valid in every thread.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -97,10 +97,15 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   __syncthreads();
   if (lane == 0) scratch[warp] = v;
   __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  double t = 0.0;
-  for (int i = 0; i < nw; ++i) t += scratch[i];
-  return t;
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = lane < nw ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
 }
 
 }  // namespace oo

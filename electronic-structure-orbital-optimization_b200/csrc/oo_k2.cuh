@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   __shared__ double s_part[NW][R][Np];
   __shared__ double s_e[R][Np];
-  __shared__ double scratch[32];
+  __shared__ double scratch[33];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int xl0 = blockIdx.x * R, N = p.N;
@@ -431,7 +431,7 @@ __global__ void k_rotate_g(const double* __restrict__ T3, const double* __restri
 // h'[i][j] = sum_{p in shard, q} U[p][i] h[p][q] U[q][j].  grid N*N, block 128.
 __global__ void k_rotate_h(const double* __restrict__ h, const double* __restrict__ U,
                            double* __restrict__ hout, int M, int N, int t0, int Mloc) {
-  __shared__ double scratch[32];
+  __shared__ double scratch[33];
   const int i = blockIdx.x / N, j = blockIdx.x % N;
   double s = 0.0;
   for (int idx = threadIdx.x; idx < Mloc * M; idx += blockDim.x) {

@@ -149,6 +149,7 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
     for (int idx = tid; idx < nn; idx += nth) {
       const int i = idx / n, j = idx - i * n;
       double s = 0.0;
+#pragma unroll 4
       for (int m = 0; m < n; ++m) s = fma(Z[i * LD + m], Y[m * LD + j], s);
       const double d = s - ((i == j) ? 1.0 : 0.0);
       r = fma(d, d, r);
@@ -163,6 +164,7 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
       if (idx < nn) {
         const int i = idx / n, j = idx - i * n;
         double sy = 0.0, sz = 0.0;
+#pragma unroll 4
         for (int m = 0; m < n; ++m) {
           sy = fma(Y[i * LD + m], W[m * LD + j], sy);
           sz = fma(W[i * LD + m], Z[m * LD + j], sz);
@@ -281,7 +283,7 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
 
 __global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uout, int M, int N) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
-      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
   retract_cta(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
 }
@@ -301,7 +303,7 @@ struct StepParams {
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
 __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
-      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
   OptState* st = p.st;
   if (st->done) return;
@@ -386,7 +388,7 @@ struct BBParams {
 };
 __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
-      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[32];
+      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
   const int tid = threadIdx.x, nth = blockDim.x, MN = p.M * p.N;
   double alpha = *p.alpha_io;
