@@ -201,7 +201,16 @@ def main():
         eng.set_integrals(h, g, assume_v4_symmetric=True)   # symmetric by construction
         esoo_b200.attach_nccl(eng)
         if args.allreduce == "fused":
-            esoo_b200.attach_peer_memory(eng)
+            try:
+                esoo_b200.attach_peer_memory(eng)
+            except Exception as exc:            # no peer access on this box: NCCL still works
+                if rank == 0:
+                    print(f"# fused all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+                args.allreduce = "nccl"
+            flag = torch.tensor([1 if args.allreduce == "fused" else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0 and args.allreduce == "fused":
+                raise SystemExit("ranks disagree on the all-reduce mode")
     eng.set_rdms(D, G)
     eng.set_pair_symmetry(not args.dense)
     slabs = eng.streamed_slabs()
