@@ -142,8 +142,13 @@ struct oo_ctx {
   void* peer_map[PEER_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peer_on = false;
   int peer_stride = 0;
-  unsigned long long peer_seq = 0;
+  unsigned long long* peer_seq_dev = nullptr;
   int* peer_err = nullptr;
+  // CUDA graph of one chunk of optimiser transitions (oo_optimize)
+  cudaGraphExec_t chunk_graph = nullptr;
+  const void* graph_key[10] = {nullptr, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long graph_kernels = 0;
   // timing
   bool timing = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -273,7 +278,7 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
     tp.comm.rank = c->rank;
     tp.comm.world = c->world;
     tp.comm.stride = c->peer_stride;
-    tp.comm.seq = ++c->peer_seq;
+    tp.comm.seq_ptr = c->peer_seq_dev;
     tp.comm.error_flag = c->peer_err;
     for (int r = 0; r < c->world; ++r) {
       tp.comm.flags[r] = (unsigned long long*)c->peer_map[r];
@@ -552,6 +557,8 @@ int oo_destroy(oo_ctx* c) {
     if (c->Gp_slot[s2]) cudaFree(c->Gp_slot[s2]);
   if (c->peer_base) cudaFree(c->peer_base);
   if (c->peer_err) cudaFree(c->peer_err);
+  if (c->peer_seq_dev) cudaFree(c->peer_seq_dev);
+  if (c->chunk_graph) cudaGraphExecDestroy(c->chunk_graph);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
                     c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};
@@ -899,15 +906,59 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   int slot = 0;
   bool pending[2] = {false, false};
   bool done = false;
-  auto enqueue_chunk = [&](int s) -> int {
+  auto chunk_body = [&]() -> int {
     int rc;
     for (int i = 0; i < chunk; ++i) {
       if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag, true))) return rc;
       k_step<<<1, K3_THREADS, 0, c->stream>>>(sp);
       CU_TRY(cudaGetLastError());
       c->launches++;
-      ++enq;
     }
+    return OO_OK;
+  };
+  // The chunk (4 x [one-body | K1, q-contraction, tail(+all-reduce), step]) is captured once into
+  // a CUDA graph and replayed: the inner loop of small problems is launch-bound.  The first chunk
+  // runs un-captured (it also performs the one-time function-attribute calls).
+  const bool use_graph = !c->timing && getenv("OO_NO_GRAPH") == nullptr;
+  const void* key[10] = {c->E_hist, (const void*)(uintptr_t)c->hist_cap, c->stream, c->g, c->g2,
+                         c->h, c->comm, (const void*)(uintptr_t)(c->pair_sym + 2 * c->generic +
+                                                                 4 * c->peer_on),
+                         c->Gp_slot[0], (const void*)(uintptr_t)c->world};
+  bool first_chunk = true;
+  auto enqueue_chunk = [&](int s) -> int {
+    int rc;
+    if (!use_graph || first_chunk) {
+      if ((rc = chunk_body())) return rc;
+      first_chunk = false;
+    } else {
+      if (c->chunk_graph && memcmp(key, c->graph_key, sizeof key) != 0) {
+        cudaGraphExecDestroy(c->chunk_graph);
+        c->chunk_graph = nullptr;
+      }
+      if (!c->chunk_graph) {
+        const long long before = c->launches;
+        CU_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        rc = chunk_body();
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess)
+          return fail(OO_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&c->chunk_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess)
+          return fail(OO_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        c->graph_kernels = c->launches - before;
+        c->launches = before;
+        memcpy(c->graph_key, key, sizeof key);
+      }
+      CU_TRY(cudaGraphLaunch(c->chunk_graph, c->stream));
+      c->launches += c->graph_kernels;
+    }
+    enq += chunk;
     CU_TRY(cudaMemcpyAsync(&c->pin_state[s], c->state, sizeof(OptState), cudaMemcpyDeviceToHost,
                            c->stream));
     CU_TRY(cudaEventRecord(c->poll_ev[s], c->stream));
@@ -987,6 +1038,8 @@ int oo_peer_export(oo_ctx* c, void* handle64_host) {
     CU_TRY(cudaMemset(c->peer_base, 0, bytes));
     CU_TRY(cudaMalloc((void**)&c->peer_err, sizeof(int)));
     CU_TRY(cudaMemset(c->peer_err, 0, sizeof(int)));
+    CU_TRY(cudaMalloc((void**)&c->peer_seq_dev, sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(c->peer_seq_dev, 0, sizeof(unsigned long long)));
     CU_TRY(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;

@@ -256,7 +256,8 @@ struct PeerComm {
   double* slots[PEER_MAX];               // rank r's slot area (peer-mapped)
   unsigned long long* flags[PEER_MAX];   // rank r's flag area (peer-mapped)
   int* error_flag;                       // set on wait time-out (never hang the GPU)
-  unsigned long long seq;
+  unsigned long long* seq_ptr;           // device-resident evaluation counter (same on all ranks;
+                                         // kept on the device so the launch can live in a CUDA graph)
   int rank, world, enabled;
   int stride;                            // doubles per slot (>= M*N+1)
 };
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
       // ---- fused one-shot all-reduce of out[0 .. M*N] over peer memory ----
       __syncthreads();
       const PeerComm& cm = p.comm;
-      const int len = p.M * N + 1, par = (int)(cm.seq & 1ull);
+      const unsigned long long seq = *cm.seq_ptr + 1ull;
+      const int len = p.M * N + 1, par = (int)(seq & 1ull);
       const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
       for (int idx = tid; idx < len; idx += TAIL_THREADS) {
         const double val = __ldcg(p.out + idx);
@@ -388,11 +390,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
       __threadfence_system();
       __syncthreads();
       if (tid < cm.world)
-        *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = cm.seq;
+        *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = seq;
       if (tid < cm.world) {
         volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
         const long long t_start = clock64();
-        while (*f < cm.seq) {
+        while (*f < seq) {
           if (clock64() - t_start > 4000000000ll) {   // ~2 s: give up instead of hanging
             *cm.error_flag = 1;
             break;
@@ -407,6 +409,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
         for (int r = 0; r < cm.world; ++r) s += __ldcg(mine + (size_t)r * cm.stride + idx);
         p.out[idx] = s;
       }
+      __syncthreads();                 // everybody has read *seq_ptr
+      if (tid == 0) *cm.seq_ptr = seq;
     }
   }
 }
