@@ -550,6 +550,12 @@ int oo_destroy(oo_ctx* c) {
   if (!c) return OO_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  // a graph that captured NCCL work must go before the communicator it refers to
+  if (c->chunk_graph) {
+    cudaGraphExecDestroy(c->chunk_graph);
+    c->chunk_graph = nullptr;
+  }
+  if (c->aux) cudaStreamSynchronize(c->aux);
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   for (int r = 0; r < PEER_MAX; ++r)
     if (c->peer_map[r] && c->peer_map[r] != c->peer_base) cudaIpcCloseMemHandle(c->peer_map[r]);
@@ -558,7 +564,6 @@ int oo_destroy(oo_ctx* c) {
   if (c->peer_base) cudaFree(c->peer_base);
   if (c->peer_err) cudaFree(c->peer_err);
   if (c->peer_seq_dev) cudaFree(c->peer_seq_dev);
-  if (c->chunk_graph) cudaGraphExecDestroy(c->chunk_graph);
   double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
                     c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};

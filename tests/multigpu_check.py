@@ -26,7 +26,9 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (M, N, pair) in [(64, 16, True), (64, 16, False), (50, 5, True), (272, 8, True)]:
+    cases = [(64, 16, True), (64, 16, False), (50, 5, True), (272, 8, True)]
+    cases = cases[:int(os.environ.get("OO_MG_CASES", len(cases)))]
+    for (M, N, pair) in cases:
         h = synthetic.h_spatial(M)
         D, G = synthetic.rdms_spatial(N)
         U = synthetic.random_partial_unitary(M, N)
@@ -48,6 +50,9 @@ def main():
                 esoo_b200.attach_peer_memory(eng)
             for rep in range(3):            # several evaluations: exercises both flag parities
                 E, g = eng.energy_grad(U)
+            if os.environ.get("OO_MG_VERBOSE"):
+                print(f"[rank {rank}] {mode}: evaluations done, peer_status="
+                      f"{eng.peer_status() if mode == 'fused' else '-'}", flush=True)
             dE = abs(float(E) - float(E_ref))
             dg = float((g - g_ref).norm() / g_ref.norm())
             # identical bits on every rank in fused mode (fixed summation order)
@@ -56,6 +61,8 @@ def main():
             dist.all_gather(allv, vec)
             same = all(torch.equal(allv[0], v) for v in allv)
             o = eng.optimize(U.numpy(), 0.02, 1e-9, 40)
+            if os.environ.get("OO_MG_VERBOSE"):
+                print(f"[rank {rank}] {mode}: optimize done n_iter={o['n_iter']}", flush=True)
             dopt = abs(o["energy"] - o_ref["energy"])
             good = dE <= 1e-10 * max(1.0, abs(float(E_ref))) and dg <= 1e-9 and \
                 o["n_iter"] == o_ref["n_iter"] and dopt <= 1e-8 and (same or mode == "nccl")
