@@ -78,6 +78,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Non-blocking arrival on a named barrier (producer side of an arrive/sync pair).
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Shared-memory vector loads with explicit 32-bit shared addresses.
 __device__ __forceinline__ void lds128(double& x, double& y, uint32_t addr) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));

@@ -16,7 +16,8 @@
 //                                                 the 8x8 C fragment of m8n8k4 is two 8x4 A
 //                                                 fragments with a permuted k order), B = U^T (smem)
 // Work decomposition: persistent CTAs (one per SM), slabs dealt round-robin; inside a CTA one TMA
-// producer warp and 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
+// producer warp, one epilogue warp (per-slab reduction + stores, off the MMA critical path) and
+// 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
 // the current 256-row pass and all of its columns, so the second contraction costs a fixed N/M
 // fraction of the first.
 #pragma once
@@ -29,7 +30,10 @@ constexpr int K1_RB = 4;                           // 8-row blocks per consumer 
 constexpr int K1_ROWS = K1_NWARP * K1_RB * 8;      // slab rows per pass = TMA box height (256)
 constexpr int K1_KC = 16;                          // slab columns per stage (128 B swizzle span)
 constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
-constexpr int K1_THREADS = (K1_NWARP + 1) * 32;    // + 1 producer warp
+constexpr int K1_THREADS = (K1_NWARP + 2) * 32;    // + 1 TMA producer warp + 1 epilogue warp
+constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
+constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
+constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + epilogue warp
 
 struct K1Params {
   const double* U;       // [M][N] row-major partial unitary
@@ -129,7 +133,7 @@ __device__ __forceinline__ void k1_second_gemm(double (&yacc)[NT][NT][2],
   }
 }
 
-// 9 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
+// 10 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
 // 65536 / 384 = 168 per thread; NT <= 2 needs ~142, NT = 3 fits, NT = 4 spills a little.
 template <int NT>
 __global__ void __launch_bounds__(K1_THREADS, 1)
@@ -198,6 +202,30 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
           }
         }
       }
+    }
+    return;
+  }
+
+  if (warp == K1_NWARP + 1) {
+    // ------------------------------ epilogue warp ------------------------------
+    // Takes the per-slab reduction off the consumers' critical path: they only drop their
+    // partial tiles into shared memory and go on with the next slab; this warp sums the 8
+    // partials in fixed order (deterministic) and stores the tile and its transpose.
+    named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);           // the buffer starts out free
+    for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+      named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
+      double* out = p.Y + (size_t)slab * Np * Np;
+      double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
+      for (int e = lane; e < Np * Np; e += 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < K1_NWARP; ++w) s += Ypart[w * Np * Np + e];
+        out[e] = s;
+        // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
+        // reads both orientations with unit stride
+        if (outT) outT[(e % Np) * Np + e / Np] = s;
+      }
+      named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
     }
     return;
   }
@@ -290,8 +318,8 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
                          ut_base + uoff_b + (uint32_t)((pass * K1_ROWS + warp * 8) * 8),
                          u_nt_stride, nact);
       if (pass == npass - 1) {
-        // ---- end of slab: fixed-order reduction of the 8 per-warp partials, store Y^T ----
-        named_bar_sync(1, K1_NWARP * 32);  // previous slab's readers are done with Ypart
+        // ---- end of slab: hand the per-warp partial tile to the epilogue warp ----
+        named_bar_sync(K1_BAR_FREE, K1_BAR_COUNT);   // previous slab's tile has been consumed
         double* mine = Ypart + warp * Np * Np;
 #pragma unroll
         for (int nl = 0; nl < NT; ++nl)
@@ -301,18 +329,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
             *reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c) = v;
             yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
           }
-        named_bar_sync(1, K1_NWARP * 32);
-        double* out = p.Y + (size_t)slab * Np * Np;
-        double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
-        for (int e = tid; e < Np * Np; e += K1_NWARP * 32) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < K1_NWARP; ++w) s += Ypart[w * Np * Np + e];
-          out[e] = s;
-          // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
-          // reads both orientations with unit stride
-          if (outT) outT[(e % Np) * Np + e / Np] = s;
-        }
+        named_bar_arrive(K1_BAR_FULL, K1_BAR_COUNT);
       }
     }
 
