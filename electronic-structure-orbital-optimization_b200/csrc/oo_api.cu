@@ -491,7 +491,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->B1, (size_t)mloc * N);
   A(&c->B12, (size_t)mloc * N);
   A(&c->T3, (size_t)M * c->Np * Np2);
-  A(&c->Gp, (size_t)N * c->Np * Np2);
+  A(&c->Gp, (size_t)c->Np * c->Np * Np2);
   A(&c->D, (size_t)N * N);
   A(&c->A, (size_t)M * N);
   A(&c->UD, MN);
@@ -646,7 +646,7 @@ int oo_set_integrals_generic(oo_ctx* c, const double* h_dev, const double* g_dev
   if (rc) return rc;
   if ((rc = build_tmap(c, c->g2, &c->tmap2))) return rc;
   if (!c->Gp_slot[0]) {
-    const size_t n = (size_t)c->N * c->Np * c->Np * c->Np;
+    const size_t n = (size_t)c->Np * c->Np * c->Np * c->Np;
     for (int s = 0; s < 4; ++s) {
       CU_TRY(cudaMalloc((void**)&c->Gp_slot[s], n * sizeof(double)));
       CU_TRY(cudaMemset(c->Gp_slot[s], 0, n * sizeof(double)));

@@ -34,7 +34,7 @@ __global__ void k_v4_symmetry(const double* __restrict__ g, int M, unsigned long
   }
 }
 
-// Gp[a][j][l*Np+k] = (1/4)(G[a,j,k,l] + G[j,a,l,k] + G[k,l,a,j] + G[l,k,j,a])  (V4 average),
+// Logical Gp[a][j][l*Np+k] = (1/4)(G[a,j,k,l] + G[j,a,l,k] + G[k,l,a,j] + G[l,k,j,a])  (V4 average),
 // zero in the padding (j, k or l >= N).  grid N*Np, block Np*Np threads (looped).
 // symmetrise = 0 selects one of the four slot layouts of the generic (no symmetry) gradient:
 //   slot 0: Gp[a][j][l*Np+k] = G[a,j,k,l]      slot 1: Gp[a][i][l*Np+k] = G[i,a,k,l]
@@ -60,7 +60,10 @@ __global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict
         v *= 0.25;
       }
     }
-    Gp[((size_t)a * Np + j) * Np2 + e] = v;
+    // storage: a fastest, Gp[(j*Np2 + e)*Np + a] (rows a >= N stay zero from the allocation):
+    // the tail kernel reads all a of one (j,e) with unit stride; strides of Np^3 doubles between
+    // the a-planes made every CTA hit the same L2 slices at the same time (measured 10x slower)
+    Gp[((size_t)j * Np2 + e) * Np + a] = v;
   }
 }
 

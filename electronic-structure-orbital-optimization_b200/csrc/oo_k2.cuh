@@ -265,7 +265,7 @@ struct PeerComm {
 struct TailParams {
   PeerComm comm;
   const double* T3;    // [nrows][Np^3]
-  const double* Gp;    // [N][Np^3]
+  const double* Gp;    // [Np^3][Np]: 2-RDM, a fastest (see k_prepare_gamma)
   const double* U;     // [M][N]
   const double* B1;    // [mloc][N]  one-body rows of the shard
   const double* B12;   // [mloc][N]
@@ -307,19 +307,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
 #pragma unroll
   for (int r = 0; r < R; ++r) tp[r] = p.T3 + (size_t)min(xl0 + r, p.nrows - 1) * L;
 #pragma unroll 2
-  for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
-    double2 tv[R];
+  for (int idx = tid; idx < L; idx += TAIL_THREADS) {
+    double tv[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) tv[r] = *reinterpret_cast<const double2*>(tp[r] + idx);
+    for (int r = 0; r < R; ++r) tv[r] = tp[r][idx];
+    const double2* gq = reinterpret_cast<const double2*>(p.Gp + (size_t)idx * Np);
 #pragma unroll
-    for (int a = 0; a < Np; ++a) {
-      if (a < N) {
-        const double2 gv = __ldg(reinterpret_cast<const double2*>(p.Gp + (size_t)a * L + idx));
+    for (int a2 = 0; a2 < Np / 2; ++a2) {
+      const double2 gv = __ldg(gq + a2);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acc[r][a] = fma(tv[r].x, gv.x, acc[r][a]);
-          acc[r][a] = fma(tv[r].y, gv.y, acc[r][a]);
-        }
+      for (int r = 0; r < R; ++r) {
+        acc[r][2 * a2] = fma(tv[r], gv.x, acc[r][2 * a2]);
+        acc[r][2 * a2 + 1] = fma(tv[r], gv.y, acc[r][2 * a2 + 1]);
       }
     }
   }
