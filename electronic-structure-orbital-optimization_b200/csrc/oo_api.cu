@@ -303,8 +303,9 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.nrows = pair ? c->M : c->mloc;
   tp.two_body_grad_factor = slot < 0 ? 4.0 : 1.0;
   tp.accumulate = slot > 0 ? 1 : 0;
-  constexpr int R = tail_rows(NT);
-  k_tail_row<NT><<<(tp.nrows + R - 1) / R, TAIL_THREADS, 0, c->stream>>>(tp);
+  constexpr int R = tail_rows(NT), AC = tail_ac(NT);
+  dim3 grid((tp.nrows + R - 1) / R, (NT * 8) / AC);
+  k_tail_row<NT><<<grid, TAIL_THREADS, 0, c->stream>>>(tp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
@@ -496,7 +497,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->A, (size_t)M * N);
   A(&c->UD, MN);
   A(&c->UDt, MN);
-  A(&c->rowE, M);
+  A(&c->rowE, (size_t)4 * M);
   A(&c->out, MN + 1);
   A(&c->Ucur, MN);
   A(&c->Uprev, MN);

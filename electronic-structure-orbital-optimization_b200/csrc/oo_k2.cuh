@@ -270,7 +270,7 @@ struct TailParams {
   const double* B1;    // [mloc][N]  one-body rows of the shard
   const double* B12;   // [mloc][N]
   double* out;         // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
-  double* rowE;        // [nrows]
+  double* rowE;        // [Np/AC][nrows] per-row energy partials
   unsigned int* counter;
   const int* done_flag;
   int M, N, t0, mloc;  // shard: the one-body terms are added for rows in [t0, t0+mloc) only
@@ -280,66 +280,72 @@ struct TailParams {
 };
 
 constexpr int TAIL_THREADS = 256;
-// rows per CTA: the 2-RDM is read once per CTA, so more rows = less L2 traffic; bounded by registers
-__host__ __device__ constexpr int tail_rows(int NT) { return NT <= 2 ? 4 : (NT == 3 ? 2 : 1); }
+// Register blocking of the 2-RDM contraction: R rows x AC a-values per CTA (grid.y = Np / AC).
+// The 2-RDM is re-read from L2 once per CTA row-group and the T3 rows once per a-chunk, so the
+// L2 traffic is nrows/R * |Gp| + Np/AC * |T3|; R*AC accumulators live in registers.
+__host__ __device__ constexpr int tail_rows(int NT) { return NT <= 2 ? 4 : 8; }
+__host__ __device__ constexpr int tail_ac(int NT) { return NT >= 1 ? 8 : 8; }
 
-// grid ceil(nrows / R), block 256.  For the R rows x of the CTA:
+// grid (ceil(nrows / R), Np / AC), block 256.  For the R rows x and the AC values a of the CTA:
 //   A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                 (2-RDM contraction)
-//   out[x]  = 4 A[x] + B12[x] (own rows),   rowE[x] = U[x].(A[x] + B1[x])
+//   out[x][a] = 4 A[x][a] + B12[x][a] (own rows),   rowE[y][x] = sum_a U[x][a] (A + B1)[x][a]
 // and the last CTA adds rowE in fixed order into out[M*N].
 template <int NT>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
-  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32, R = tail_rows(NT);
+  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32, R = tail_rows(NT),
+                AC = tail_ac(NT);
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ double s_part[NW][R][Np];
-  __shared__ double s_e[R][Np];
+  __shared__ double s_part[NW][R][AC];
+  __shared__ double s_e[R][AC];
   __shared__ double scratch[33];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int xl0 = blockIdx.x * R, N = p.N;
+  const int xl0 = blockIdx.x * R, a0 = blockIdx.y * AC, N = p.N;
 
-  double acc[R][Np];
+  double acc[R][AC];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int a = 0; a < Np; ++a) acc[r][a] = 0.0;
+    for (int a = 0; a < AC; ++a) acc[r][a] = 0.0;
   const double* tp[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) tp[r] = p.T3 + (size_t)min(xl0 + r, p.nrows - 1) * L;
+  // each thread takes two consecutive (j,e) positions per step: 16-byte loads everywhere
 #pragma unroll 2
-  for (int idx = tid; idx < L; idx += TAIL_THREADS) {
-    double tv[R];
+  for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
+    double2 tv[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) tv[r] = tp[r][idx];
-    const double2* gq = reinterpret_cast<const double2*>(p.Gp + (size_t)idx * Np);
+    for (int r = 0; r < R; ++r) tv[r] = *reinterpret_cast<const double2*>(tp[r] + idx);
+    const double2* g0 = reinterpret_cast<const double2*>(p.Gp + (size_t)idx * Np + a0);
+    const double2* g1 = reinterpret_cast<const double2*>(p.Gp + (size_t)(idx + 1) * Np + a0);
 #pragma unroll
-    for (int a2 = 0; a2 < Np / 2; ++a2) {
-      const double2 gv = __ldg(gq + a2);
+    for (int a2 = 0; a2 < AC / 2; ++a2) {
+      const double2 u = __ldg(g0 + a2), v = __ldg(g1 + a2);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        acc[r][2 * a2] = fma(tv[r], gv.x, acc[r][2 * a2]);
-        acc[r][2 * a2 + 1] = fma(tv[r], gv.y, acc[r][2 * a2 + 1]);
+        acc[r][2 * a2] = fma(tv[r].x, u.x, fma(tv[r].y, v.x, acc[r][2 * a2]));
+        acc[r][2 * a2 + 1] = fma(tv[r].x, u.y, fma(tv[r].y, v.y, acc[r][2 * a2 + 1]));
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int a = 0; a < Np; ++a) {
+    for (int a = 0; a < AC; ++a) {
       double v = acc[r][a];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) s_part[warp][r][a] = v;
     }
   __syncthreads();
-  if (tid < R * Np) {
-    const int r = tid / Np, a = tid - r * Np;
+  if (tid < R * AC) {
+    const int r = tid / AC, al = tid - r * AC, a = a0 + al;
     const int xl = xl0 + r, x = p.row0 + xl;
     double ev = 0.0;
     if (xl < p.nrows && a < N) {
       double av = 0.0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) av += s_part[w][r][a];
+      for (int w = 0; w < NW; ++w) av += s_part[w][r][al];
       const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
       double b1 = 0.0, b12 = 0.0;
       if (mine) {
@@ -350,26 +356,27 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
       else p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
       ev = __ldg(p.U + (size_t)x * N + a) * (av + b1);
     }
-    s_e[r][a] = ev;
+    s_e[r][al] = ev;
   }
   __syncthreads();
   if (tid == 0) {
     for (int r = 0; r < R; ++r) {
       if (xl0 + r < p.nrows) {
         double e = 0.0;
-        for (int a = 0; a < N; ++a) e += s_e[r][a];
-        p.rowE[xl0 + r] = e;
+        for (int a = 0; a < AC; ++a) e += s_e[r][a];
+        p.rowE[(size_t)blockIdx.y * p.nrows + xl0 + r] = e;
       }
     }
     __threadfence();
     const unsigned int prev = atomicAdd(p.counter, 1u);
-    is_last = (prev == (unsigned int)(gridDim.x - 1));
+    is_last = (prev == (unsigned int)(gridDim.x * gridDim.y - 1));
   }
   __syncthreads();
   if (is_last) {
     __threadfence();
     double v = 0.0;
-    for (int i = tid; i < p.nrows; i += TAIL_THREADS) v += ((volatile double*)p.rowE)[i];
+    for (int i = tid; i < p.nrows * (int)gridDim.y; i += TAIL_THREADS)
+      v += ((volatile double*)p.rowE)[i];
     v = block_sum(v, scratch);                  // fixed tree: deterministic
     if (tid == 0) {
       if (!p.accumulate) p.out[(size_t)p.M * N] = v;
