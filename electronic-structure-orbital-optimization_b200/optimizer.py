@@ -107,15 +107,24 @@ class PartialUnitaryProjectionOptimizer:
         dev = self._torch_device()
         # The outer loops re-create the device tensors every iteration (.to(device) / .to('cpu'),
         # opt_orb_minimum_eigensolver.py:219-235), so identity is useless as a key: use a content
-        # fingerprint (one streaming pass, negligible next to the H2D copy the caller just paid).
-        h_dev, g_dev = one_body_integrals.to(dev), two_body_integrals.to(dev)
-        flat = g_dev.reshape(-1)
-        key = (dev.index, tuple(g_dev.shape), self._n_active, float(flat.sum()),
-               float(flat[::7].sum()), float(flat.abs().max()), float(h_dev.sum()))
+        # fingerprint computed WHERE THE TENSOR LIVES, so that a cache hit costs neither an H2D copy
+        # of the (2M)^4 tensor nor a re-ingest.  Device tensors: full sums (one streaming pass);
+        # host tensors: a 1 % strided sample plus the one-body sum.
+        g_src, h_src = two_body_integrals, one_body_integrals
+        flat = g_src.reshape(-1)
+        if g_src.is_cuda:
+            fp = (float(flat.sum()), float(flat[::7].sum()), float(flat.abs().max()))
+        else:
+            sample = flat[::101]
+            fp = (float(sample.sum()), float(sample.abs().sum()), float(flat[-1]))
+        key = (dev.index, str(g_src.device.type), tuple(g_src.shape), self._n_active, fp,
+               float(h_src.sum()))
         hit = _ENGINE_CACHE.get(key)
         if hit is not None:
             return hit
+        h_dev, g_dev = one_body_integrals.to(dev), two_body_integrals.to(dev)
         h_sp, g_sp, structure = ingest.reduce_integrals_device(h_dev, g_dev)
+        del g_dev
         while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
             old_key = next(iter(_ENGINE_CACHE))
             _ENGINE_CACHE.pop(old_key)[0].close()
