@@ -665,7 +665,12 @@ int oo_check_v4_symmetry(int device, const double* g_dev, int M, double* out_hos
   unsigned long long* d = nullptr;
   CU_TRY(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
   CU_TRY(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
-  k_v4_symmetry<<<148 * 8, 256>>>(g_dev, M, d);
+  {
+    const int T = (M + 31) / 32;
+    dim3 grid((unsigned)((long)M * (M + 1) / 2), T, T), block(32, 8);
+    k_v4_symmetry_tiles<0><<<grid, block>>>(g_dev, M, d);
+    k_v4_symmetry_tiles<1><<<grid, block>>>(g_dev, M, d);
+  }
   cudaError_t e = cudaGetLastError();
   unsigned long long hbits[2] = {0, 0};
   if (e == cudaSuccess) e = cudaMemcpy(hbits, d, sizeof hbits, cudaMemcpyDeviceToHost);
