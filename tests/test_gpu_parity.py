@@ -523,3 +523,54 @@ def test_device_ingest_matches_torch_ingest(torch_cuda, pattern):
     assert abs(float(E1) - float(E2)) <= 1e-12 * max(1.0, abs(float(E1)))
     assert _rel(g_2.cpu().numpy(), g_1.cpu().numpy()) <= 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("maxiter", [0, 1, 2, 3, 4, 7])
+def test_optimizer_small_maxiter_matches_oracle(torch_cuda, maxiter):
+    """The three hand-unrolled iterations always run and the loop test is `k <= maxiter`
+    (pupo.py:191-304): same iteration count, energy and U as the oracle for tiny maxiter."""
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    M, N = 14, 3
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=9)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    res = eng.optimize(U.numpy(), 0.02, 1e-14, maxiter)
+    hn, gn, Dn, Gn = h.numpy(), g.numpy(), D.numpy(), G.numpy()
+    ref = onp.optimal_rotation(lambda X: onp.rotated_energy_spatial(X, Dn, Gn, hn, gn),
+                               lambda X: onp.rotated_energy_grad_spatial(X, Dn, Gn, hn, gn),
+                               U.numpy(), 0.02, 1e-14, maxiter)
+    assert res["n_iter"] == ref["n_iter"] == max(3, maxiter + 1)
+    assert abs(res["energy"] - ref["energy"]) <= 1e-10
+    assert np.max(np.abs(res["U"] - ref["U"])) <= 1e-9
+    assert abs(res["stepsize"] - ref["stepsize"]) <= 1e-9 * max(1.0, abs(ref["stepsize"]))
+    eng.close()
+
+
+def test_call_sequence_errors(torch_cuda):
+    """The C layer reports misuse through status codes + oo_last_error (no abort, no fallback)."""
+    import esoo_b200
+    from esoo_b200._lib import OOError
+    torch = torch_cuda
+    M, N = 8, 2
+    h, g, D, G, U = _spatial_case(torch, M, N)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    with pytest.raises(OOError, match="oo_set_integrals"):
+        eng.energy_grad(U)
+    eng.set_integrals(h, g)
+    with pytest.raises(OOError, match="oo_set_rdms"):
+        eng.energy_grad(U)
+    with pytest.raises(ValueError):
+        eng.set_rdms(D[:1], G)
+    with pytest.raises(TypeError):
+        eng.set_rdms(D.float(), G.float())
+    eng.set_rdms(D, G)
+    E, _ = eng.energy_grad(U)
+    assert np.isfinite(float(E))
+    eng.close()
+    with pytest.raises(OOError):
+        esoo_b200.OrbitalEngine(4, 8, device="cuda:0")          # N > M
+    with pytest.raises(OOError):
+        esoo_b200.OrbitalEngine(80, 40, device="cuda:0")        # N > 32
