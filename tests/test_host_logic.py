@@ -290,3 +290,20 @@ def test_outer_goldens_present():
         # the orbital optimisation lowers the (state-averaged) energy at the first outer step
         w = g["weights"][:E.shape[1]]
         assert float(E[1] @ w) < float(E[0] @ w)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/oo_b200.h is a C ABI: it must compile as C99 with no CUDA / C++ / torch types."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "oo_b200.h"\n'
+                   'int probe(void) { oo_ctx* c = 0; double e; (void)c;\n'
+                   '  return oo_create(0, 8, 2, 0, 8, &c) + oo_energy_grad_host(c, 0, &e, 0); }\n')
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-c", str(src), "-I",
+                          os.path.join(ROOT, "include"), "-o", str(tmp_path / "abi.o")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
