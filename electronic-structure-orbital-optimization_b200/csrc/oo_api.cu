@@ -155,6 +155,7 @@ struct oo_ctx {
   float last_ms[5] = {0, 0, 0, 0, 0};
   long long launches = 0;
   int last_ns_iters = 0, last_jacobi_calls = 0;   // telemetry of the last oo_optimize
+  int force_jacobi = 0;   // OO_FORCE_JACOBI=1: retraction through the eigensolver path only
 };
 
 namespace {
@@ -464,6 +465,10 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   c->t0 = t0;
   c->mloc = mloc;
   c->num_sms = prop.multiProcessorCount;
+  {
+    const char* fj = getenv("OO_FORCE_JACOBI");
+    c->force_jacobi = (fj && *fj && *fj != '0') ? 1 : 0;
+  }
   c->Mk = (M + K1_KC - 1) / K1_KC * K1_KC;
   // deepest TMA ring that fits 227 KiB
   c->nstage = 0;
@@ -835,7 +840,7 @@ int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_ro
 int oo_orth(oo_ctx* c, const double* V_dev, double* U_out_dev) {
   if (!c || !V_dev || !U_out_dev) return fail(OO_ERR_INVALID, "NULL argument");
   CU_TRY(cudaSetDevice(c->device));
-  k_orth<<<1, K3_THREADS, 0, c->stream>>>(V_dev, U_out_dev, c->M, c->N);
+  k_orth<<<1, K3_THREADS, 0, c->stream>>>(V_dev, U_out_dev, c->M, c->N, c->force_jacobi);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
@@ -860,6 +865,7 @@ int oo_bb_update(oo_ctx* c, int iteration, const double* U_cur_dev, const double
   p.iteration = iteration;
   p.M = c->M;
   p.N = c->N;
+  p.force_jacobi = c->force_jacobi;
   k_bb_update<<<1, K3_THREADS, 0, c->stream>>>(p);
   CU_TRY(cudaGetLastError());
   c->launches++;
@@ -906,6 +912,7 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   sp.M = c->M;
   sp.N = c->N;
   sp.hist_cap = c->hist_cap;
+  sp.force_jacobi = c->force_jacobi;
   const int* done_flag = &c->state->done;
 
   // Transitions are enqueued in chunks; the stop flag of chunk i is inspected while chunk i+1

@@ -199,7 +199,8 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
 // scratch 32 doubles.
 __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
                                    double* sB1, double* sB2, double* sB3, double* cs,
-                                   double* scratch, int* sflag, int* telemetry = nullptr) {
+                                   double* scratch, int* sflag, int* telemetry = nullptr,
+                                   bool force_jacobi = false) {
   constexpr int LD = K3_NMAX + 1;
   const int tid = threadIdx.x, nth = blockDim.x;
   // Gram matrix V^T V: the t-range is split over nth / N^2 thread groups, partials summed in
@@ -239,7 +240,8 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
   double scale = 1.0;
   double* S = sB2;  // inverse square root (up to `scale`) ends up here
   int ns_it = 0;
-  const bool ok = newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale, &ns_it);
+  const bool ok = !force_jacobi &&
+                  newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale, &ns_it);
   if (telemetry && tid == 0) {
     telemetry[0] += ns_it;
     if (!ok) telemetry[1] += 1;
@@ -281,11 +283,12 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uout, int M, int N) {
+__global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uout, int M, int N,
+                                                      int force_jacobi) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
       sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
-  retract_cta(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
+  retract_cta(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr, force_jacobi != 0);
 }
 
 struct StepParams {
@@ -298,6 +301,7 @@ struct StepParams {
   double* E_hist;       // E_hist[k] = f(U_k)
   int M, N;
   int hist_cap;
+  int force_jacobi;     // debugging / testing: skip Newton-Schulz, use the eigensolver path
 };
 
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
@@ -371,7 +375,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
     p.Gprev[i] = g;
   }
   __syncthreads();
-  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, &st->ns_iters);
+  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, &st->ns_iters,
+              p.force_jacobi != 0);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
 // Standalone BB update (compute_updated_partial_unitary, pupo.py:129-159) for API parity.
 struct BBParams {
   const double* Ucur; const double* Uprev; const double* Gcur; const double* Gprev;
-  double* Unew; double* Vtmp; double* alpha_io; int iteration; int M, N;
+  double* Unew; double* Vtmp; double* alpha_io; int iteration; int M, N; int force_jacobi;
 };
 __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
@@ -409,7 +414,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   }
   for (int i = tid; i < MN; i += nth) p.Vtmp[i] = p.Ucur[i] - alpha * p.Gcur[i];
   __syncthreads();
-  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag);
+  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
+              p.force_jacobi != 0);
   if (tid == 0) *p.alpha_io = alpha;
 }
 

@@ -574,3 +574,29 @@ def test_call_sequence_errors(torch_cuda):
         esoo_b200.OrbitalEngine(4, 8, device="cuda:0")          # N > M
     with pytest.raises(OOError):
         esoo_b200.OrbitalEngine(80, 40, device="cuda:0")        # N > 32
+
+
+def test_jacobi_fallback_path(torch_cuda, monkeypatch):
+    """The retraction's eigensolver path (taken when Newton-Schulz does not converge) forced via
+    OO_FORCE_JACOBI: orth() against the reference golden and the optimiser against the oracle."""
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    monkeypatch.setenv("OO_FORCE_JACOBI", "1")
+    gold = load_golden("abba_M12_N4")
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0")
+    out = opt.orth(torch.from_numpy(gold["V"])).cpu().numpy()
+    assert np.max(np.abs(out - gold["orthV"])) <= 1e-12
+    M, N = 24, 9
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=4)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    res = eng.optimize(U.numpy(), 0.02, 1e-9, 60)
+    assert res["jacobi_fallbacks"] == res["n_iter"] and res["newton_schulz_iterations"] == 0
+    hn, gn, Dn, Gn = h.numpy(), g.numpy(), D.numpy(), G.numpy()
+    ref = onp.optimal_rotation(lambda X: onp.rotated_energy_spatial(X, Dn, Gn, hn, gn),
+                               lambda X: onp.rotated_energy_grad_spatial(X, Dn, Gn, hn, gn),
+                               U.numpy(), 0.02, 1e-9, 60)
+    assert res["n_iter"] == ref["n_iter"] and abs(res["energy"] - ref["energy"]) <= EFINAL_TOL
+    eng.close()
