@@ -156,6 +156,10 @@ struct oo_ctx {
   long long launches = 0;
   int last_ns_iters = 0, last_jacobi_calls = 0;   // telemetry of the last oo_optimize
   int force_jacobi = 0;   // OO_FORCE_JACOBI=1: retraction through the eigensolver path only
+  // live callback of oo_optimize (pupo.py:193-194, 226-227, 260-261, 312-313)
+  oo_callback_t cb = nullptr;
+  void* cb_user = nullptr;
+  double* pin_hist = nullptr;   // 2 slots x chunk energies
 };
 
 namespace {
@@ -533,6 +537,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   if (e == cudaSuccess) e = cudaMemset(c->state, 0, sizeof(OptState));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin, (MN + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin_state, 2 * sizeof(OptState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->pin_hist, 2 * 8 * sizeof(double));
   // A blocking stream: it orders itself against the legacy default stream, which is where a host
   // framework (torch) produces the input tensors unless told otherwise.
   if (e == cudaSuccess) e = cudaStreamCreate(&c->stream);
@@ -581,6 +586,7 @@ int oo_destroy(oo_ctx* c) {
   if (c->state) cudaFree(c->state);
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_state) cudaFreeHost(c->pin_state);
+  if (c->pin_hist) cudaFreeHost(c->pin_hist);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->poll_ev)
@@ -943,6 +949,23 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
                                                                  4 * c->peer_on),
                          c->Gp_slot[0], (const void*)(uintptr_t)c->world};
   bool first_chunk = true;
+  long chunk_start[2] = {0, 0};
+  double prev_f = 0.0;          // f(U_{k-1}) carried across chunks for the callback replay
+  static_assert(4 <= 8, "pin_hist holds up to 8 energies per slot");
+  // Callbacks are delivered while the device keeps running: at every flag poll the energies of
+  // the chunk that just finished are handed out with the reference's arguments
+  // (k <= 2: (k, f(U_k)); loop iterations k >= 3: (k, f(U_{k-1})), pupo.py:313).
+  auto deliver_callbacks = [&](int s) {
+    if (!c->cb) return;
+    const OptState& stt = c->pin_state[s];
+    const long n_exec = stt.done ? stt.k_final : stt.k;   // transitions whose body ran
+    const double* hst = c->pin_hist + s * 8;
+    for (long k = chunk_start[s]; k < chunk_start[s] + chunk && k < n_exec; ++k) {
+      const double fk = hst[k - chunk_start[s]];
+      c->cb((int)k, k <= 2 ? fk : prev_f, c->cb_user);
+      prev_f = fk;
+    }
+  };
   auto enqueue_chunk = [&](int s) -> int {
     int rc;
     if (!use_graph || first_chunk) {
@@ -976,6 +999,10 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
       CU_TRY(cudaGraphLaunch(c->chunk_graph, c->stream));
       c->launches += c->graph_kernels;
     }
+    chunk_start[s] = enq;
+    if (c->cb && enq + chunk <= c->hist_cap)
+      CU_TRY(cudaMemcpyAsync(c->pin_hist + s * 8, c->E_hist + enq, chunk * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
     enq += chunk;
     CU_TRY(cudaMemcpyAsync(&c->pin_state[s], c->state, sizeof(OptState), cudaMemcpyDeviceToHost,
                            c->stream));
@@ -992,6 +1019,7 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
     }
     CU_TRY(cudaEventSynchronize(c->poll_ev[slot]));
     pending[slot] = false;
+    deliver_callbacks(slot);
     if (c->pin_state[slot].done) {
       done = true;
     } else if (!pending[other]) {
@@ -1015,6 +1043,13 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   c->last_ns_iters = fin.ns_iters;
   c->last_jacobi_calls = fin.jacobi_calls;
   if (fin.nan_flag) return fail(OO_ERR_NUMERIC, "non-finite value met during the optimisation");
+  return OO_OK;
+}
+
+int oo_set_callback(oo_ctx* c, oo_callback_t cb, void* user) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  c->cb = cb;
+  c->cb_user = user;
   return OO_OK;
 }
 

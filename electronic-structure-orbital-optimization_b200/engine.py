@@ -265,9 +265,14 @@ class OrbitalEngine:
         _lib.check(self.lib.oo_synchronize(self._ctx))
         return out[:self.M_user], float(alpha.item())
 
-    def optimize(self, U0, bb0: float, tol: float, maxiter: int, decay: float = 0.8):
+    def optimize(self, U0, bb0: float, tol: float, maxiter: int, decay: float = 0.8,
+                 callback=None):
         """The whole inner loop on the device.  Returns dict(U ndarray, energy, n_iter, E_hist,
-        stepsize)."""
+        stepsize).  `callback(iteration, energy)` is delivered live (at most 4 iterations late)
+        with the reference's arguments."""
+        cb_c = _lib.CALLBACK_T(lambda it, e, _u: callback(int(it), float(e))) if callback else \
+            C.cast(None, _lib.CALLBACK_T)
+        _lib.check(self.lib.oo_set_callback(self._ctx, cb_c, None))
         Uh = np.zeros((self.M, self.N), dtype=np.float64)
         Uh[:self.M_user] = np.asarray(U0, dtype=np.float64)
         cap = max(int(maxiter), 0) + 8
@@ -277,6 +282,7 @@ class OrbitalEngine:
                                         float(tol), int(maxiter), float(decay),
                                         hist.ctypes.data_as(C.c_void_p), cap, C.byref(n_iter),
                                         C.byref(E), C.byref(bb)))
+        _lib.check(self.lib.oo_set_callback(self._ctx, C.cast(None, _lib.CALLBACK_T), None))
         ns, jac = C.c_int(), C.c_int()
         _lib.check(self.lib.oo_retraction_stats(self._ctx, C.byref(ns), C.byref(jac)))
         return {"U": Uh[:self.M_user].copy(), "energy": float(E.value), "n_iter": int(n_iter.value),

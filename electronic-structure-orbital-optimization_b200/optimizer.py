@@ -13,8 +13,8 @@ Differences, all deliberate:
     stopping rule run inside liboo_b200 on the GPU; there is no CPU path (device must be 'cuda*');
   * `fun` is only *identified* (compute_rotated_energy / compute_rotated_weighted_energy_sum), not
     called; an arbitrary callable raises TypeError;
-  * user callbacks are replayed, in order and with the reference's arguments, after the device
-    loop has finished (same (iteration, energy) pairs, different wall-clock moment);
+  * user callbacks are delivered in order and with the reference's arguments while the device
+    loop runs, at most one chunk (4 iterations) late (same (iteration, energy) pairs);
   * instances hold no device handles, so `copy.deepcopy` (base_opt_orb_solver.py:75) is safe;
     engines are cached in a module-level registry keyed by the integral tensors.
 """
@@ -244,16 +244,13 @@ class PartialUnitaryProjectionOptimizer:
         U0 = initial_partial_unitary.detach().to('cpu').to(torch.float64).numpy()
         if self.gradient_method == 'finite_difference':
             return self._optimal_rotation_finite_difference(eng, U0)
+        # the callback is delivered by the library while the device loop runs, with the
+        # reference's arguments: (k, f(U_k)) for k <= 2 (pupo.py:193-194, 226-227, 260-261) and
+        # (k, f(U_{k-1})) inside the loop (pupo.py:313)
         res = eng.optimize(U0, float(self._BBstepsize), float(self.stopping_tolerance),
-                           int(self.maxiter), float(self.decay_factor))
+                           int(self.maxiter), float(self.decay_factor), callback=self._callback)
         self._BBstepsize = res["stepsize"]
         self.last_result = {"n_iter": res["n_iter"], "E_hist": res["E_hist"][:res["n_iter"] + 1]}
-        if self._callback is not None:
-            hist, K = res["E_hist"], res["n_iter"]
-            for k in range(min(3, K + 1)):            # pupo.py:193-194, 226-227, 260-261
-                self._callback(k, float(hist[k]))
-            for k in range(3, K):                     # loop body reports the previous energy (:313)
-                self._callback(k, float(hist[k - 1]))
         U = torch.from_numpy(res["U"])
         return U, torch.tensor(res["energy"], dtype=torch.float64)
 

@@ -150,6 +150,12 @@ int oo_bb_update(oo_ctx* ctx, int iteration, const double* U_cur_dev, const doub
  * initial partial unitary on entry and the final one on exit; *E_final = the reference's return
  * value P4_array[0]; E_hist_host[k] = f(U_k) for k < hist_cap (callback replay);
  * *n_iter = final iteration_number. */
+/* Optional live callback of oo_optimize, the reference's callback(iteration, energy)
+ * (pupo.py:29-30): invoked on the calling host thread, in order and with the reference's
+ * arguments, at most one chunk (4 iterations) after the device produced the value, while the
+ * device keeps iterating.  NULL disables it. */
+typedef void (*oo_callback_t)(int iteration, double energy, void* user);
+int oo_set_callback(oo_ctx* ctx, oo_callback_t cb, void* user);
 int oo_optimize(oo_ctx* ctx, double* U_io_host, double bb0, double tol, int maxiter, double decay,
                 double* E_hist_host, int hist_cap, int* n_iter, double* E_final,
                 double* bb_final);
