@@ -102,7 +102,7 @@ int load_nccl() {
 // ------------------------------------------------------------------------------------------------
 struct oo_ctx {
   int device = 0, M = 0, N = 0, NT = 0, Np = 0, t0 = 0, mloc = 0;
-  int num_sms = 0, nstage = 0, Mk = 0;
+  int num_sms = 0, nstage = 0, Mk = 0, npart = 8;
   size_t k1_smem = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -215,6 +215,7 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   p.nstage = c->nstage;
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
+  p.npart = c->npart;
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[c->device & 7]) {
     CU_TRY(cudaFuncSetAttribute(k1_half_transform<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -474,19 +475,26 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     c->force_jacobi = (fj && *fj && *fj != '0') ? 1 : 0;
   }
   c->Mk = (M + K1_KC - 1) / K1_KC * K1_KC;
-  // deepest TMA ring that fits 227 KiB
+  // deepest TMA ring that fits 227 KiB; folding the 8 per-warp partial tiles into 4 or 2
+  // buffers is used only when it buys another stage
   c->nstage = 0;
-  for (int ns = 6; ns >= 2; --ns) {
-    if (k1_smem_bytes(c->NT, c->Mk, ns) <= (size_t)227 * 1024) {
-      c->nstage = ns;
-      break;
+  c->npart = K1_NWARP;
+  for (int npart : {8, 4, 2}) {
+    for (int ns = 6; ns >= 2; --ns) {
+      if (k1_smem_bytes(c->NT, c->Mk, ns, npart) <= (size_t)227 * 1024) {
+        if (ns > c->nstage) {
+          c->nstage = ns;
+          c->npart = npart;
+        }
+        break;
+      }
     }
   }
   if (!c->nstage) {
     delete c;
     return fail(OO_ERR_UNSUPPORTED, "M=%d N=%d does not fit the K1 shared-memory plan", M, N);
   }
-  c->k1_smem = k1_smem_bytes(c->NT, c->Mk, c->nstage);
+  c->k1_smem = k1_smem_bytes(c->NT, c->Mk, c->nstage, c->npart);
   const size_t MN = (size_t)M * N, Np2 = (size_t)c->Np * c->Np;
   auto alloc = [&](double** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(double)); };
   cudaError_t e = cudaSuccess;

@@ -1,5 +1,5 @@
 // Input preparation kernels: permutation-symmetry verification of the ERI tensor and the
-// symmetrised / padded / permuted copy of the 2-RDM consumed by k_gamma_contract.
+// symmetrised / padded / permuted copy of the 2-RDM consumed by k_tail_row, spin-orbital ingest.
 #pragma once
 #include "oo_common.cuh"
 

@@ -33,6 +33,7 @@ constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
 constexpr int K1_THREADS = (K1_NWARP + 2) * 32;    // + 1 TMA producer warp + 1 epilogue warp
 constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
 constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
+constexpr int K1_BAR_FOLD = 3;                     // named barrier: consumers only, between fold rounds
 constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + epilogue warp
 
 struct K1Params {
@@ -48,14 +49,16 @@ struct K1Params {
   int nstage;            // TMA ring depth
   int Mk;                // M rounded up to a multiple of K1_KC
   int upitch;            // row pitch (doubles) of the transposed U copy in smem: Mk + 8
+  int npart;             // partial-tile buffers at slab end: 8 (one per warp), 4 or 2 (warps are
+                         // folded into them in fixed order; frees smem for one more TMA stage)
 };
 
 // Dynamic shared memory needed by k1_half_transform<NT> (before 1024 B alignment slack).
-static inline size_t k1_smem_bytes(int NT, int Mk, int nstage) {
+static inline size_t k1_smem_bytes(int NT, int Mk, int nstage, int npart = K1_NWARP) {
   const int Np = NT * 8;
   size_t b = (size_t)nstage * K1_STAGE_BYTES;           // TMA ring
   b += (size_t)Np * (Mk + 8) * sizeof(double);          // Ut
-  b += (size_t)K1_NWARP * Np * Np * sizeof(double);     // per-warp partial Y
+  b += (size_t)npart * Np * Np * sizeof(double);        // partial-tile buffers (8, 4 or 2)
   b += (size_t)2 * nstage * sizeof(uint64_t);           // full/empty mbarriers
   return b + 1024;                                      // alignment slack
 }
@@ -146,7 +149,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       (reinterpret_cast<uintptr_t>(k1_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   double* Ut = reinterpret_cast<double*>(smem + (size_t)p.nstage * K1_STAGE_BYTES);
   double* Ypart = Ut + (size_t)Np * p.upitch;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ypart + K1_NWARP * Np * Np);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ypart + p.npart * Np * Np);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t stage_base = smem_u32(smem);
@@ -218,8 +221,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
       for (int e = lane; e < Np * Np; e += 32) {
         double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < K1_NWARP; ++w) s += Ypart[w * Np * Np + e];
+        for (int w = 0; w < p.npart; ++w) s += Ypart[w * Np * Np + e];
         out[e] = s;
         // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
         // reads both orientations with unit stride
@@ -320,15 +322,30 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       if (pass == npass - 1) {
         // ---- end of slab: hand the per-warp partial tile to the epilogue warp ----
         named_bar_sync(K1_BAR_FREE, K1_BAR_COUNT);   // previous slab's tile has been consumed
-        double* mine = Ypart + warp * Np * Np;
+        // warps w, w+npart, w+2*npart, ... share buffer w % npart; they are folded in rounds
+        // (fixed order => deterministic), separated by a consumer-only barrier
+        double* mine = Ypart + (warp % p.npart) * Np * Np;
+        const int rounds = K1_NWARP / p.npart;
+        for (int rnd = 0; rnd < rounds; ++rnd) {
+          if (warp / p.npart == rnd) {
 #pragma unroll
-        for (int nl = 0; nl < NT; ++nl)
+            for (int nl = 0; nl < NT; ++nl)
 #pragma unroll
-          for (int nk = 0; nk < NT; ++nk) {
-            double2 v = make_double2(yacc[nl][nk][0], yacc[nl][nk][1]);
-            *reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c) = v;
-            yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
+              for (int nk = 0; nk < NT; ++nk) {
+                double2* dst =
+                    reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c);
+                double2 v = make_double2(yacc[nl][nk][0], yacc[nl][nk][1]);
+                if (rnd > 0) {
+                  const double2 o = *dst;
+                  v.x += o.x;
+                  v.y += o.y;
+                }
+                *dst = v;
+                yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
+              }
           }
+          if (rnd + 1 < rounds) named_bar_sync(K1_BAR_FOLD, K1_NWARP * 32);
+        }
         named_bar_arrive(K1_BAR_FULL, K1_BAR_COUNT);
       }
     }

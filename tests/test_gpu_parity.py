@@ -236,10 +236,11 @@ def _shard_partial_oracle(gsh, t0, U, D, G, h, pair_symmetric):
 
 @pytest.mark.parametrize("pair_symmetric", [False, True])
 @pytest.mark.parametrize("M,N,t0,mloc", [(272, 8, 268, 4), (400, 24, 100, 2), (264, 16, 0, 3),
-                                         (40, 5, 11, 7)])
+                                         (40, 5, 11, 7), (600, 24, 37, 1)])
 def test_multipass_shard_vs_oracle(torch_cuda, M, N, t0, mloc, pair_symmetric):
     """M > 256 exercises the second 256-row pass of K1 (partially filled row-blocks) on a thin
-    shard of the first index, in both slab modes; the oracle contracts the same slabs."""
+    shard of the first index, in both slab modes; the oracle contracts the same slabs.  M=400
+    and M=600 with N=24 also exercise the folded partial-tile buffers (4 and 2 instead of 8)."""
     import esoo_b200
     from esoo_b200 import synthetic
     torch = torch_cuda
