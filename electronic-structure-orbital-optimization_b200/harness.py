@@ -131,13 +131,17 @@ def run_outer_loop(optimizer, h: torch.Tensor, g: torch.Tensor, num_spin_orbital
                    n_states: int = 1, weights: Optional[Sequence[float]] = None,
                    initial_partial_unitary: Optional[torch.Tensor] = None,
                    energy_impl: Optional[Callable] = None, engine_for_transform=None,
-                   outer_loop_callback: Optional[Callable] = None):
+                   outer_loop_callback: Optional[Callable] = None,
+                   state_indices: Optional[Sequence[int]] = None):
     """Exact-diagonalisation version of OptOrbMinimumEigensolver.compute_minimum_energy (n_states=1)
     / OptOrbEigensolver.compute_energies (n_states>1, state-averaged with `weights`).
 
     h, g: the reference's spin-orbital integral tensors ([2M,2M], [2M]^4, float64, CPU).
     energy_impl: the Python objective handed to optimisers that *call* `fun` (the reference class);
-    the CUDA optimiser never calls it.  Returns dict(energies=[per outer iteration: list of state
+    the CUDA optimiser never calls it.  state_indices picks which eigenvectors of the (S_z-resolved)
+    active-space Hamiltonian play the role of the k states (default: the k lowest); e.g. (0, 2)
+    skips the S_z = 0 triplet component that a singlet-preserving ansatz cannot reach.
+    Returns dict(energies=[per outer iteration: list of state
     energies], U=final partial unitary, inner_iterations=[...])."""
     P = h.shape[0]
     M, Q = P // 2, num_spin_orbitals
@@ -173,11 +177,12 @@ def run_outer_loop(optimizer, h: torch.Tensor, g: torch.Tensor, num_spin_orbital
         H = sector.hamiltonian(h_rot, g_rot)
         evals, evecs = np.linalg.eigh(H[np.ix_(sub, sub)])
         states = []
-        for n in range(n_states):
+        picks = list(state_indices) if state_indices is not None else list(range(n_states))
+        for n in picks:
             psi = np.zeros(len(sector.dets))
             psi[sub] = evecs[:, n]
             states.append(psi)
-        energies.append([float(e) for e in evals[:n_states]])
+        energies.append([float(evals[n]) for n in picks])
         if outer_loop_callback is not None:
             outer_loop_callback(it, energies[-1], U)
         if stop(it):

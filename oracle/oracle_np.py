@@ -8,7 +8,10 @@ must never be imported by the product package: only ``tests/``, ``__graft_entry_
 Parity status: the reference's own tests hold no tensor-level golden vectors for this path
 (SURVEY.md section 8c).  The oracle is therefore pinned against outputs of the *live* reference
 code, loaded from /root/reference by ``oracle/ref_loader.py`` and frozen as fixtures under
-``tests/golden/`` by ``tests/golden/make_golden.py``.
+``tests/golden/`` by ``tests/golden/make_golden.py``.  The end-to-end numbers hard-coded in the
+reference's tests (H2 / 6-31G: tests/test_optorbvqe.py:67, tests/test_optorbmcvqe.py:61) are
+reproduced too, with this oracle as the optimiser inside the exact-diagonalisation outer loop
+(tests/test_oracle_golden.py::test_oracle_outer_loop_on_molecule).
 
 Reference files restated here (paths under electronic_structure_algorithms/orbital_optimization/):
   base_opt_orb_solver.py:534-582   compute_rotated_energy          -> rotated_energy_spin

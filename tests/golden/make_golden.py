@@ -144,7 +144,47 @@ def main_outer():
                             U_final=res["U"].numpy())
 
 
+# ------------------------------------------------------------------------------------------------
+# the reference's OWN test system: H2, 0.735 Angstrom, 6-31G, 4 spin orbitals (M = 4, N = 2), with
+# the optimiser settings of its tests.  `ref_test_golden` is the number hard-coded in the
+# reference's test file; the run below (exact diagonalisation instead of VQE, live reference
+# optimiser) lands on it, which pins integrals, conventions, harness and optimiser end to end.
+# ------------------------------------------------------------------------------------------------
+MOLECULE_CASES = [
+    # name, atoms, N, n_states, weights, reference test golden (file:line)
+    ("outer_H2_631G_ground", 2, 2, 1, None, [-1.8661038079694765]),     # tests/test_optorbvqe.py:67
+    ("outer_H2_631G_k2", 2, 2, 2, [2, 1], [-1.85703467, -1.46615986]),  # tests/test_optorbmcvqe.py:61
+    ("outer_H4_631G_ground", 4, 4, 1, None, None),                      # no golden: H4 chain, M = 8
+]
+
+
+def main_molecule():
+    from esoo_b200 import harness, molecule
+    Pupo, _ = ref_loader.load_reference()
+    for (name, atoms, N, k, weights, ref_gold) in MOLECULE_CASES:
+        mol = molecule.hydrogen_chain(atoms, 0.735)
+        hs, gs = synthetic.spin_orbital_integrals(mol["h"], mol["g"], "abba")
+        M = mol["h"].shape[0]
+        solver = ref_loader.make_solver(True, weights)
+        bb0, tol, imax, omax, otol = 1e-3, 1e-5, 10000, 20, 1e-5     # tests/test_optorbvqe.py:72-90
+        opt = Pupo(initial_BBstepsize=bb0, stopping_tolerance=tol, maxiter=imax)
+        res = harness.run_outer_loop(opt, hs, gs, 2 * N, atoms // 2, atoms // 2, maxiter=omax,
+                                     stopping_tolerance=otol, n_states=k, weights=weights,
+                                     energy_impl=solver.compute_rotated_energy)
+        E = np.array(res["energies"], dtype=np.float64)
+        print(f"{name}: outer iterations {len(E)}, final {E[-1]}, reference test golden {ref_gold}")
+        extra = {} if ref_gold is None else {"ref_test_golden": np.array(ref_gold)}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), M=M, N=N, n_alpha=atoms // 2,
+                            n_beta=atoms // 2, n_states=k,
+                            weights=np.array(weights if weights else [1.0]),
+                            outer_maxiter=omax, outer_tol=otol, bb0=bb0, tol=tol, maxiter=imax,
+                            h_spin=hs.numpy(), g_spin=gs.numpy(), energies=E,
+                            U_final=res["U"].numpy(), e_nuc=mol["e_nuc"], e_hf=mol["e_hf"], **extra)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "molecule":
+        main_molecule()
     if len(sys.argv) < 2 or sys.argv[1] == "inner":
         main()
     if len(sys.argv) < 2 or sys.argv[1] == "outer":

@@ -72,3 +72,101 @@ def test_optimal_rotation_trajectory(name):
     Es = np.array([c[1] for c in res["callbacks"]])
     assert np.max(np.abs(Es - gold["opt_calls_E"])) <= 1e-7
     assert np.max(np.abs(res["U"] - gold["opt_U"])) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own test system (H2, 0.735 Angstrom, 6-31G -> 4 spin orbitals) and the numbers
+# hard-coded in its test files.  pyscf / qiskit are absent, so the integrals come from the closed
+# forms in esoo_b200.molecule and the eigensolver from the exact-diagonalisation harness.
+# ---------------------------------------------------------------------------------------------
+def test_h2_631g_integrals():
+    from esoo_b200 import molecule, synthetic, harness
+    mol = molecule.hydrogen_chain(2, 0.735)
+    h, g = mol["h"].numpy(), mol["g"].numpy()
+    assert h.shape == (4, 4) and g.shape == (4, 4, 4, 4)
+    assert abs(mol["e_nuc"] - 0.52917721092 / 0.735) < 1e-12
+    # literature values for H2 / 6-31G at 0.735 Angstrom: RHF -1.1268, FCI -1.1516 (total energies)
+    assert abs(mol["e_hf"] + mol["e_nuc"] + 1.12681) < 5e-5
+    # MO basis: Fock matrix diagonal => Brillouin: h is not diagonal, but the 8-fold symmetry of
+    # (pq|rs) must hold for g[p,q,r,s] = -1/2 (ps|qr)
+    eri = -2.0 * g.transpose(0, 3, 1, 2)                     # (ps|qr) -> eri[p,s,q,r]
+    for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)]:
+        assert np.max(np.abs(eri - eri.transpose(perm))) < 1e-13
+    # HF energy from the MO integrals: 2 h_00 + (00|00)
+    assert abs(2 * h[0, 0] + eri[0, 0, 0, 0] - mol["e_hf"]) < 1e-10
+    # full CI in all 8 spin orbitals
+    hs, gs = synthetic.spin_orbital_integrals(mol["h"], mol["g"], "abba")
+    sec = harness.FockSector(8, 2)
+    sub = sec.sz_subspace(1, 4)
+    H = sec.hamiltonian(hs.numpy(), gs.numpy())
+    e_fci = np.linalg.eigvalsh(H[np.ix_(sub, sub)])[0]
+    assert abs(e_fci + mol["e_nuc"] + 1.15161) < 5e-5
+    assert e_fci < mol["e_hf"]
+
+
+REF_TEST_CASES = ["outer_H2_631G_ground", "outer_H2_631G_k2"]
+
+
+@pytest.mark.parametrize("name", REF_TEST_CASES)
+def test_fixture_matches_reference_test_golden(name):
+    """The live-reference run frozen in the fixture reproduces the number hard-coded in the
+    reference's own tests (tests/test_optorbvqe.py:67,98-100 and tests/test_optorbmcvqe.py:61,96-98;
+    their assertion is decimal=3, i.e. 1.5e-3)."""
+    gold = load_golden(name)
+    final, ref = gold["energies"][-1], gold["ref_test_golden"]
+    assert np.max(np.abs(final - ref)) < 1.5e-3            # the reference's own bar
+    assert np.max(np.abs(final - ref)) < 2e-5              # what is actually achieved
+    # the stored integrals are what esoo_b200.molecule produces today
+    from esoo_b200 import molecule, synthetic
+    mol = molecule.hydrogen_chain(2, 0.735)
+    hs, gs = synthetic.spin_orbital_integrals(mol["h"], mol["g"], "abba")
+    assert np.max(np.abs(hs.numpy() - gold["h_spin"])) < 1e-12
+    assert np.max(np.abs(gs.numpy() - gold["g_spin"])) < 1e-12
+
+
+class _OracleOptimizer:
+    """The optimiser protocol of the reference (device, compute_optimal_rotation keyword call)
+    served by the numpy oracle; lets the harness run without the reference tree."""
+    device = "cpu"
+
+    def __init__(self, bb0, tol, maxiter):
+        self.bb0, self.tol, self.maxiter = bb0, tol, maxiter
+
+    def compute_optimal_rotation(self, fun, initial_partial_unitary, oneRDM, twoRDM,
+                                 one_body_integrals, two_body_integrals):
+        import torch
+        hs, gs = one_body_integrals.numpy(), two_body_integrals.numpy()
+        if isinstance(oneRDM, list):
+            w = list(fun.__self__.weight_vector)
+            Ds, Gs = [d.numpy() for d in oneRDM], [g.numpy() for g in twoRDM]
+            e = lambda U: onp.weighted_energy_sum_spin(U, Ds, Gs, hs, gs, w)
+            gr = lambda U: onp.weighted_energy_grad_spin(U, Ds, Gs, hs, gs, w)
+        else:
+            D, G = oneRDM.numpy(), twoRDM.numpy()
+            e = lambda U: onp.rotated_energy_spin(U, D, G, hs, gs)
+            gr = lambda U: onp.rotated_energy_grad_spin(U, D, G, hs, gs)
+        res = onp.optimal_rotation(e, gr, initial_partial_unitary.numpy(), self.bb0, self.tol,
+                                   self.maxiter)
+        return torch.from_numpy(res["U"]), torch.tensor(res["energy"], dtype=torch.float64)
+
+
+@pytest.mark.parametrize("name", REF_TEST_CASES + ["outer_H4_631G_ground"])
+def test_oracle_outer_loop_on_molecule(name):
+    """Oracle optimiser inside the outer loop: every outer energy within 1e-8 Ha of the run with
+    the live reference optimiser, hence on the reference's test goldens."""
+    import torch
+    from esoo_b200 import harness
+    gold = load_golden(name)
+    k, N = int(gold["n_states"]), int(gold["N"])
+    weights = list(gold["weights"]) if k > 1 else None
+    opt = _OracleOptimizer(float(gold["bb0"]), float(gold["tol"]), int(gold["maxiter"]))
+    res = harness.run_outer_loop(opt, torch.from_numpy(gold["h_spin"]), torch.from_numpy(gold["g_spin"]),
+                                 2 * N, int(gold["n_alpha"]), int(gold["n_beta"]),
+                                 maxiter=int(gold["outer_maxiter"]),
+                                 stopping_tolerance=float(gold["outer_tol"]), n_states=k,
+                                 weights=weights)
+    E = np.array(res["energies"])
+    assert E.shape == gold["energies"].shape
+    assert np.max(np.abs(E - gold["energies"])) <= 1e-8
+    if "ref_test_golden" in gold:
+        assert np.max(np.abs(E[-1] - gold["ref_test_golden"])) < 2e-5
