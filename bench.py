@@ -166,7 +166,12 @@ def main():
                          "memory (default) or a separate NCCL call")
     ap.add_argument("--dense", action="store_true",
                     help="stream every slab of the shard instead of one per (t,q)/(q,t) pair")
+    ap.add_argument("--packed", action="store_true",
+                    help="pair-packed ERI storage (OO_G_PAIR_PACKED): only the streamed slab of "
+                         "every (t,q)/(q,t) pair is resident, half the memory (M=400 fits one GPU)")
     args = ap.parse_args()
+    if args.packed and args.dense:
+        raise SystemExit("--packed stores only the pair-symmetric slab set; it excludes --dense")
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -192,13 +197,18 @@ def main():
     M, N, K, W = args.M, args.N, args.steps, max(3, args.warmup)
     t0, mloc = esoo_b200.shard_range(M, rank, world)
     h = synthetic.h_spatial(M, device=dev)
-    g = synthetic.eri_spatial_shard(M, t0, mloc, device=dev)
     D, G = synthetic.rdms_spatial(N)
     eng = esoo_b200.OrbitalEngine(M, N, device=dev, t0=t0, mloc=mloc)
-    if world == 1:
-        eng.set_integrals(h, g)                # verifies the V4 symmetry on the device
+    if args.packed:
+        g = synthetic.eri_spatial_pair_packed(M, t0, mloc, device=dev)
+        eng.set_integrals_packed(h, g)         # symmetric by construction (half is not stored)
     else:
-        eng.set_integrals(h, g, assume_v4_symmetric=True)   # symmetric by construction
+        g = synthetic.eri_spatial_shard(M, t0, mloc, device=dev)
+        if world == 1:
+            eng.set_integrals(h, g)            # verifies the V4 symmetry on the device
+        else:
+            eng.set_integrals(h, g, assume_v4_symmetric=True)   # symmetric by construction
+    if world > 1:
         esoo_b200.attach_nccl(eng)
         if args.allreduce == "fused":
             try:
@@ -212,7 +222,8 @@ def main():
             if int(flag.item()) == 0 and args.allreduce == "fused":
                 raise SystemExit("ranks disagree on the all-reduce mode")
     eng.set_rdms(D, G)
-    eng.set_pair_symmetry(not args.dense)
+    if not args.packed:
+        eng.set_pair_symmetry(not args.dense)
     slabs = eng.streamed_slabs()
     stream = torch.cuda.Stream(device=dev)
     eng.use_stream(stream)
@@ -317,9 +328,14 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if (M, N) == (M_BENCH, N_BENCH) else
                        f"synthetic 8-fold-symmetric ERI M={M}, N={N}",
-                       "M": M, "N": N, "eri_shard_bytes_per_gpu": 8.0 * mloc * M ** 3,
+                       "M": M, "N": N,
+                       "eri_shard_bytes_per_gpu": float(g.numel() * 8),
+                       "storage": "pair-packed (streamed slabs only)" if args.packed else
+                       "dense first-index shard",
                        "slab_mode": "dense" if args.dense else
-                       "pair-symmetric (one slab per (t,q)/(q,t) pair, symmetry verified on device)",
+                       "pair-symmetric (one slab per (t,q)/(q,t) pair" +
+                       (", symmetry verified on device)" if world == 1 and not args.packed else
+                        ", symmetric by construction)"),
                        "slabs_streamed_per_eval_per_gpu": slabs,
                        "eri_bytes_streamed_per_eval_per_gpu": alg_bytes,
                        "sharding": f"ERI first index over {world} GPU(s), rows/GPU={mloc}",

@@ -19,10 +19,11 @@ SYMBOLS = [
     "oo_launch_count", "oo_measure_peaks", "oo_set_pair_symmetry", "oo_streamed_slabs",
     "oo_ingest_spin_g", "oo_set_rdms_spin", "oo_energy_grad_allreduce", "oo_peer_export",
     "oo_peer_attach", "oo_peer_status", "oo_set_integrals_generic",
-    "oo_retraction_stats", "oo_set_callback",
+    "oo_retraction_stats", "oo_set_callback", "oo_pair_slab_list", "oo_pack_pair_slabs",
 ]
 
 OO_G_V4_SYMMETRIC = 1
+OO_G_PAIR_PACKED = 2
 CALLBACK_T = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
 
 _lib = None
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
     lib.oo_set_callback.argtypes = [vp, CALLBACK_T, vp]
     lib.oo_set_pair_symmetry.argtypes = [vp, C.c_int]
     lib.oo_streamed_slabs.argtypes = [vp]
+    lib.oo_pair_slab_list.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int]
+    lib.oo_pack_pair_slabs.argtypes = [vp, vp, vp]
     lib.oo_ingest_spin_g.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.POINTER(C.c_uint), dp]
     lib.oo_set_rdms_spin.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), dp, C.c_int, C.c_uint]
     for name in SYMBOLS:

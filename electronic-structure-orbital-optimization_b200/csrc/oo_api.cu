@@ -110,6 +110,7 @@ struct oo_ctx {
   const double* g = nullptr;
   const double* g2 = nullptr;          // generic mode: pair-transposed tensor g2[r,s,p,q] = g[p,q,r,s]
   bool generic = false;                // no V4 symmetry: two dense passes, four gradient slots
+  bool packed = false;                 // g holds only the pair-selected slabs, in streaming order
   alignas(64) CUtensorMap tmap2;
   double* Gp_slot[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned gflags = 0;
@@ -183,12 +184,14 @@ int get_encode_fn(encode_tiled_t* fn) {
   return OO_OK;
 }
 
-// 3-D view of the shard: (s: M, r: M, slab: mloc*M), box 16 x 256 x 1, 128B swizzle, zero fill.
-int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map) {
+// 3-D view of the shard: (s: M, r: M, slab: nslab), box 16 x 256 x 1, 128B swizzle, zero fill.
+// nslab = mloc*M for dense storage, the number of stored slabs for pair-packed storage.
+int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map, size_t nslab = 0) {
+  if (nslab == 0) nslab = (size_t)c->mloc * c->M;
   encode_tiled_t enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
-  const cuuint64_t dims[3] = {(cuuint64_t)c->M, (cuuint64_t)c->M, (cuuint64_t)c->mloc * c->M};
+  const cuuint64_t dims[3] = {(cuuint64_t)c->M, (cuuint64_t)c->M, (cuuint64_t)nslab};
   const cuuint64_t strides[2] = {(cuuint64_t)c->M * 8, (cuuint64_t)c->M * c->M * 8};
   const cuuint32_t box[3] = {K1_KC, K1_ROWS, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -210,7 +213,7 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   p.done_flag = done_flag;
   p.M = c->M;
   p.N = c->N;
-  p.slab_coord = pair ? c->slab_coord : nullptr;
+  p.slab_coord = (pair && !c->packed) ? c->slab_coord : nullptr;   // packed: slab i is stored i-th
   p.nslab = pair ? c->nsel : c->mloc * c->M;
   p.nstage = c->nstage;
   p.Mk = c->Mk;
@@ -641,13 +644,47 @@ int oo_set_integrals(oo_ctx* c, const double* h_dev, const double* g_dev, unsign
                 "two-body tensors without V4 symmetry (g[pqrs]=g[qpsr]=g[rspq]) need the "
                 "pair-transposed copy as well: use oo_set_integrals_generic");
   CU_TRY(cudaSetDevice(c->device));
+  const bool packed = (flags & OO_G_PAIR_PACKED) != 0;
+  int rc = build_tmap(c, g_dev, &c->tmap, packed ? (size_t)c->nsel : 0);
+  if (rc) return rc;
   c->h = h_dev;
   c->g = g_dev;
   c->gflags = flags;
-  int rc = build_tmap(c, c->g, &c->tmap);
-  if (rc) return rc;
   c->generic = false;
+  c->packed = packed;
+  if (packed && !c->pair_sym) {
+    // packed storage only holds what the pair-symmetric mode streams
+    if ((rc = oo_set_pair_symmetry(c, 1))) return rc;
+  }
   c->have_ints = true;
+  return OO_OK;
+}
+
+int oo_pair_slab_list(int M, int t0, int mloc, int* tq_host, int capacity) {
+  if (M < 1 || t0 < 0 || mloc < 1 || t0 + mloc > M) return fail(OO_ERR_INVALID, "bad shard");
+  long n = 0;
+  for (int t = t0; t < t0 + mloc; ++t) {
+    const int cnt = pair_row_count(t, M);
+    for (int i = 0; i < cnt; ++i, ++n) {
+      if (tq_host && n < capacity) {
+        tq_host[2 * n] = t;
+        tq_host[2 * n + 1] = pair_ith_q(t, i);
+      }
+    }
+  }
+  if (tq_host && n > capacity) return fail(OO_ERR_INVALID, "tq_host holds %d of %ld slabs", capacity, n);
+  return (int)n;
+}
+
+int oo_pack_pair_slabs(oo_ctx* c, const double* g_dense_dev, double* g_packed_dev) {
+  if (!c || !g_dense_dev || !g_packed_dev) return fail(OO_ERR_INVALID, "NULL argument");
+  if ((((uintptr_t)g_dense_dev) | ((uintptr_t)g_packed_dev)) & 15)
+    return fail(OO_ERR_INVALID, "g must be 16-byte aligned");
+  CU_TRY(cudaSetDevice(c->device));
+  const int chunks = std::max(1, std::min(64, (int)(((size_t)c->M * c->M / 2 + 255) / 256)));
+  k_pack_slabs<<<dim3(c->nsel, chunks), 256, 0, c->stream>>>(g_dense_dev, g_packed_dev,
+                                                            c->slab_coord, c->M);
+  CU_TRY(cudaGetLastError());
   return OO_OK;
 }
 
@@ -662,6 +699,7 @@ int oo_set_integrals_generic(oo_ctx* c, const double* h_dev, const double* g_dev
   c->g = g_dev;
   c->g2 = g_pair_transposed_dev;
   c->gflags = 0;
+  c->packed = false;
   int rc = build_tmap(c, c->g, &c->tmap);
   if (rc) return rc;
   if ((rc = build_tmap(c, c->g2, &c->tmap2))) return rc;
@@ -954,7 +992,7 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   const bool use_graph = !c->timing && getenv("OO_NO_GRAPH") == nullptr;
   const void* key[10] = {c->E_hist, (const void*)(uintptr_t)c->hist_cap, c->stream, c->g, c->g2,
                          c->h, c->comm, (const void*)(uintptr_t)(c->pair_sym + 2 * c->generic +
-                                                                 4 * c->peer_on),
+                                                                 4 * c->peer_on + 8 * c->packed),
                          c->Gp_slot[0], (const void*)(uintptr_t)c->world};
   bool first_chunk = true;
   long chunk_start[2] = {0, 0};
@@ -1151,6 +1189,8 @@ int oo_allreduce(oo_ctx* c, double* buf_dev, size_t count) {
 
 int oo_set_pair_symmetry(oo_ctx* c, int enable) {
   if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  if (!enable && c->packed)
+    return fail(OO_ERR_STATE, "pair-packed integrals hold only the pair-symmetric slab set");
   CU_TRY(cudaSetDevice(c->device));
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->pair_sym = enable != 0;

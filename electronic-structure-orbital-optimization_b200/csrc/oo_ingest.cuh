@@ -98,6 +98,19 @@ __global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict
   }
 }
 
+// Pair-packed storage: packed[i] = dense slab coord[i] (M*M doubles each, 16-byte aligned because M
+// is even).  grid (nslab, chunks), 256 threads, 16-byte copies.
+__global__ void __launch_bounds__(256) k_pack_slabs(const double* __restrict__ dense,
+                                                    double* __restrict__ packed,
+                                                    const int* __restrict__ coord, int M) {
+  const size_t n2 = (size_t)M * M / 2;
+  const double2* src = reinterpret_cast<const double2*>(dense + (size_t)coord[blockIdx.x] * M * M);
+  double2* dst = reinterpret_cast<double2*>(packed + (size_t)blockIdx.x * M * M);
+  for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n2;
+       i += (size_t)gridDim.y * blockDim.x)
+    dst[i] = src[i];
+}
+
 }  // namespace oo
 
 namespace oo {

@@ -30,6 +30,16 @@ def pair_selected(t: int, q: int) -> bool:
     return (t < q) if ((t + q) % 2 == 0) else (t > q)
 
 
+def pair_slab_list(M: int, t0: int = 0, mloc: int = None):
+    """[(t, q), ...] of the slabs g[t, q, :, :] that pair-packed storage keeps for rows
+    [t0, t0+mloc), in storage (= streaming) order: t ascending, then q ascending (mirror of
+    oo_pair_slab_list / pair_row_count / pair_ith_q in csrc/oo_k2.cuh)."""
+    mloc = M - t0 if mloc is None else mloc
+    if t0 < 0 or mloc < 1 or t0 + mloc > M:
+        raise ValueError(f"bad shard rows [{t0}, {t0 + mloc}) of {M}")
+    return [(t, q) for t in range(t0, t0 + mloc) for q in range(M) if pair_selected(t, q)]
+
+
 def attach_nccl(engine, group=None) -> None:
     """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed
     (any backend) broadcasts its 128 bytes, every rank joins."""

@@ -133,6 +133,49 @@ class OrbitalEngine:
         self._inputs_ready()
         _lib.check(self.lib.oo_set_integrals(self._ctx, _ptr(h), _ptr(g), _lib.OO_G_V4_SYMMETRIC))
 
+    def set_integrals_packed(self, h: torch.Tensor, g_packed: torch.Tensor) -> None:
+        """Pair-packed storage of a V4-symmetric tensor: g_packed [count, M, M] holds the slabs
+        g[t, q, :, :] listed by `distributed.pair_slab_list(M, t0, mloc)` (one of every pair
+        {(t,q),(q,t)}), half the memory of the dense shard; kernel traffic is unchanged.  The
+        symmetry is asserted by the caller (it cannot be verified from half of the tensor)."""
+        if self.M != self.M_user:
+            raise ValueError("pair-packed storage needs an even M (pad the integrals first)")
+        count = self.streamed_slabs_pair()
+        if tuple(h.shape) != (self.M, self.M):
+            raise ValueError(f"h must be [{self.M},{self.M}], got {tuple(h.shape)}")
+        if tuple(g_packed.shape) != (count, self.M, self.M):
+            raise ValueError(f"g_packed must be [{count},{self.M},{self.M}], got "
+                             f"{tuple(g_packed.shape)}")
+        h, g = _dev_f64(h, self.device), _dev_f64(g_packed, self.device)
+        self.generic = False
+        self._keep["h"], self._keep["g"] = h, g
+        self._keep.pop("g_pt", None)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_set_integrals(self._ctx, _ptr(h), _ptr(g),
+                                             _lib.OO_G_V4_SYMMETRIC | _lib.OO_G_PAIR_PACKED))
+
+    def streamed_slabs_pair(self) -> int:
+        """Number of slabs of this shard in pair-packed storage (= streamed in pair mode)."""
+        n = int(self.lib.oo_pair_slab_list(self.M, self.t0, self.mloc, None, 0))
+        if n < 0:
+            _lib.check(n)
+        return n
+
+    def pack_pair_slabs(self, g: torch.Tensor) -> torch.Tensor:
+        """Gather the pair-packed shard [count, M, M] from a dense shard [mloc, M, M, M] on the
+        device (oo_pack_pair_slabs)."""
+        if self.M != self.M_user:
+            raise ValueError("pair-packed storage needs an even M (pad the integrals first)")
+        if tuple(g.shape) != (self.mloc, self.M, self.M, self.M):
+            raise ValueError(f"g must be [{self.mloc},{self.M},{self.M},{self.M}]")
+        g = _dev_f64(g, self.device)
+        out = torch.empty(self.streamed_slabs_pair(), self.M, self.M, dtype=torch.float64,
+                          device=self.device)
+        self._inputs_ready()
+        _lib.check(self.lib.oo_pack_pair_slabs(self._ctx, _ptr(g), _ptr(out)))
+        _lib.check(self.lib.oo_synchronize(self._ctx))
+        return out
+
     def set_rdms(self, D: torch.Tensor, G: torch.Tensor) -> None:
         """Spatial spin-summed (and state-weighted) D [N,N], Gamma [N,N,N,N]."""
         N = self.N

@@ -44,6 +44,25 @@ def eri_spatial_shard(M: int, t0: int, mloc: int, seed: int = SEED_ERI, rank: in
     return out
 
 
+def eri_spatial_pair_packed(M: int, t0: int = 0, mloc: int = None, seed: int = SEED_ERI,
+                            rank: int = 32, device="cpu", scale: float = 1.0) -> torch.Tensor:
+    """The same tensor in pair-packed storage: [count, M, M] with the slabs g[t, q, :, :] of
+    `distributed.pair_slab_list(M, t0, mloc)`; never materialises the dense shard."""
+    from .distributed import pair_selected
+    mloc = M - t0 if mloc is None else mloc
+    B = _factor(M, rank, seed).to(device)
+    rows = [[q for q in range(M) if pair_selected(t, q)] for t in range(t0, t0 + mloc)]
+    out = torch.empty(sum(len(r) for r in rows), M, M, dtype=torch.float64, device=device)
+    pos = 0
+    for i, qs in enumerate(rows):
+        # slab (t,q)[r,s] = -1/2 sum_L B[q,r,L] B[t,s,L]
+        Bq = B[torch.tensor(qs, device=B.device)].reshape(len(qs) * M, rank)
+        torch.matmul(Bq, B[t0 + i].transpose(0, 1), out=out[pos:pos + len(qs)].view(len(qs) * M, M))
+        pos += len(qs)
+    out.mul_(-0.5 * scale)
+    return out
+
+
 def eri_spatial(M: int, seed: int = SEED_ERI, rank: int = 32, device="cpu",
                 scale: float = 1.0) -> torch.Tensor:
     return eri_spatial_shard(M, 0, M, seed, rank, device, scale)

@@ -51,6 +51,10 @@ enum oo_status {
 #define OO_G_V4_SYMMETRIC 1u /* caller asserts g[pqrs]=g[qpsr]=g[rspq]=g[srqp] (holds for real
                                 orbitals); enables the one-pass analytic gradient              */
 
+#define OO_G_PAIR_PACKED 2u  /* with OO_G_V4_SYMMETRIC: g_dev holds only the slabs that the
+                                pair-symmetric mode streams (see oo_pair_slab_list), half the
+                                memory of the dense shard                                      */
+
 /* ---- library / device ---------------------------------------------------------------------- */
 const char* oo_last_error(void);
 const char* oo_version(void);
@@ -74,6 +78,18 @@ int oo_synchronize(oo_ctx* ctx);
  * strides are multiples of 16 bytes).  Replaces the .to(device) shuttling of the integral tensors,
  * opt_orb_minimum_eigensolver.py:219-222. */
 int oo_set_integrals(oo_ctx* ctx, const double* h_dev, const double* g_dev, unsigned flags);
+/* Pair-packed storage (flag OO_G_PAIR_PACKED).  Because g[t,q,r,s] = g[q,t,s,r], one slab of every
+ * pair {(t,q),(q,t)} carries all the information; the packed shard keeps exactly the slabs the
+ * pair-symmetric mode streams, as [slab][r][s] in streaming order (t ascending, then q ascending).
+ * 8*M*M*count bytes instead of 8*M*M*M*mloc: M=400 takes 102.4 GB (fits one 180 GB GPU) instead
+ * of 204.8 GB.  Kernel traffic and arithmetic are identical to dense storage.
+ *   oo_pair_slab_list: host-only; writes (t,q) of the i-th stored slab to tq_host[2i], [2i+1]
+ *     (tq_host may be NULL) and returns the slab count for rows [t0, t0+mloc), <0 on error.
+ *   oo_pack_pair_slabs: gathers the packed shard from a dense shard g_dense_dev [mloc][M][M][M]
+ *     on the context's stream (for callers that start from the reference's dense tensor,
+ *     base.py:89-90). */
+int oo_pair_slab_list(int M, int t0, int mloc, int* tq_host, int capacity);
+int oo_pack_pair_slabs(oo_ctx* ctx, const double* g_dense_dev, double* g_packed_dev);
 /* Two-body tensors WITHOUT V4 symmetry (single GPU only): registers g_dev [M]^4 and its
  * pair-transposed copy g_pt_dev[r][s][p][q] = g[p][q][r][s].  Every evaluation then makes two dense
  * passes (one per tensor) and builds dE/dU from the four index-slot terms, with the 2-RDM used as

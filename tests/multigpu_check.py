@@ -26,7 +26,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    cases = [(64, 16, True), (64, 16, False), (50, 5, True), (272, 8, True)]
+    # (M, N, slab mode): True = pair-symmetric, False = dense, "packed" = pair-packed storage
+    cases = [(64, 16, True), (64, 16, False), (50, 5, True), (272, 8, True), (64, 16, "packed")]
     cases = cases[:int(os.environ.get("OO_MG_CASES", len(cases)))]
     for (M, N, pair) in cases:
         h = synthetic.h_spatial(M)
@@ -37,14 +38,18 @@ def main():
         full = esoo_b200.OrbitalEngine(M, N, device=dev)
         full.set_integrals(h, synthetic.eri_spatial(M, device=dev))
         full.set_rdms(D, G)
-        full.set_pair_symmetry(pair)
+        full.set_pair_symmetry(bool(pair))
         E_ref, g_ref = full.energy_grad(U)
         o_ref = full.optimize(U.numpy(), 0.02, 1e-9, 40)
         for mode in ("nccl", "fused"):
             eng = esoo_b200.OrbitalEngine(M, N, device=dev, t0=t0, mloc=mloc)
-            eng.set_integrals(h, gsh, assume_v4_symmetric=True)
+            if pair == "packed":
+                eng.set_integrals_packed(h, synthetic.eri_spatial_pair_packed(M, t0, mloc,
+                                                                              device=dev))
+            else:
+                eng.set_integrals(h, gsh, assume_v4_symmetric=True)
+                eng.set_pair_symmetry(pair)
             eng.set_rdms(D, G)
-            eng.set_pair_symmetry(pair)
             esoo_b200.attach_nccl(eng)
             if mode == "fused":
                 esoo_b200.attach_peer_memory(eng)

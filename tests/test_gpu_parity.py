@@ -605,3 +605,54 @@ def test_jacobi_fallback_path(torch_cuda, monkeypatch):
                                U.numpy(), 0.02, 1e-9, 60)
     assert res["n_iter"] == ref["n_iter"] and abs(res["energy"] - ref["energy"]) <= EFINAL_TOL
     eng.close()
+
+
+# --------------------------------------------------------------------------------------------
+# pair-packed storage (OO_G_PAIR_PACKED): half the memory, same streamed slabs
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,t0,mloc", [(24, 4, 0, 24), (72, 16, 0, 72), (300, 8, 290, 6),
+                                         (400, 24, 100, 2), (40, 5, 11, 7)])
+def test_pair_packed_storage_is_bit_identical(torch_cuda, M, N, t0, mloc):
+    """Packed and dense storage stream the same slabs in the same order, so energy and gradient
+    agree bit for bit; the device gather (oo_pack_pair_slabs) and the slab-wise synthetic
+    generator produce the same packed tensor."""
+    import esoo_b200
+    from esoo_b200 import synthetic
+    torch = torch_cuda
+    h = synthetic.h_spatial(M)
+    gsh = synthetic.eri_spatial_shard(M, t0, mloc, device="cuda:0")
+    D, G = synthetic.rdms_spatial(N)
+    U = synthetic.random_partial_unitary(M, N)
+    dense = esoo_b200.OrbitalEngine(M, N, device="cuda:0", t0=t0, mloc=mloc)
+    dense.set_integrals(h, gsh, assume_v4_symmetric=True)
+    dense.set_rdms(D, G)
+    E0, g0 = dense.energy_grad(U)
+    packed_t = dense.pack_pair_slabs(gsh)
+    assert packed_t.shape[0] == dense.streamed_slabs() == dense.streamed_slabs_pair()
+    assert torch.equal(packed_t, synthetic.eri_spatial_pair_packed(M, t0, mloc, device="cuda:0"))
+    lst = esoo_b200.distributed.pair_slab_list(M, t0, mloc)
+    for i in (0, len(lst) // 2, len(lst) - 1):
+        t, q = lst[i]
+        assert torch.equal(packed_t[i], gsh[t - t0, q])
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0", t0=t0, mloc=mloc)
+    eng.set_integrals_packed(h, packed_t)
+    eng.set_rdms(D, G)
+    E1, g1 = eng.energy_grad(U)
+    assert float(E1) == float(E0)
+    assert torch.equal(g1, g0)
+    with pytest.raises(RuntimeError):
+        eng.set_pair_symmetry(False)              # the other half of the slabs is not stored
+    if mloc == M:
+        h0, gr0 = dense.transform(U)
+        h1, gr1 = eng.transform(U)
+        assert torch.equal(h0, h1) and torch.equal(gr0, gr1)
+        r0 = dense.optimize(U.numpy(), 0.02, 1e-9, 40)
+        r1 = eng.optimize(U.numpy(), 0.02, 1e-9, 40)
+        assert r0["n_iter"] == r1["n_iter"] and r0["energy"] == r1["energy"]
+        assert np.array_equal(r0["U"], r1["U"])
+        # back to dense storage on the same context
+        eng.set_integrals(h, gsh, assume_v4_symmetric=True)
+        E2, g2 = eng.energy_grad(U)
+        assert float(E2) == float(E0) and torch.equal(g2, g0)
+    eng.close()
+    dense.close()

@@ -307,3 +307,32 @@ def test_header_is_plain_c(tmp_path):
                           os.path.join(ROOT, "include"), "-o", str(tmp_path / "abi.o")],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_pair_packed_slab_list_and_generator():
+    """Pair-packed storage: the host-only C entry point, its Python mirror and the slab-wise
+    synthetic generator agree; the shards of the list partition the M(M+1)/2 pairs."""
+    import ctypes as C
+    import torch
+    from esoo_b200 import _lib, distributed, synthetic
+    lib = _lib.load()
+    for M, world in [(10, 1), (10, 3), (17, 4), (64, 8)]:
+        total = []
+        for r in range(world):
+            t0, mloc = distributed.shard_range(M, r, world)
+            lst = distributed.pair_slab_list(M, t0, mloc)
+            n = lib.oo_pair_slab_list(M, t0, mloc, None, 0)
+            assert n == len(lst)
+            buf = (C.c_int * (2 * n))()
+            assert lib.oo_pair_slab_list(M, t0, mloc, buf, n) == n
+            assert [(buf[2 * i], buf[2 * i + 1]) for i in range(n)] == lst
+            assert lib.oo_pair_slab_list(M, t0, mloc, buf, n - 1) < 0      # capacity too small
+            total += lst
+        assert len(total) == M * (M + 1) // 2
+        assert len({(min(t, q), max(t, q)) for t, q in total}) == len(total)   # one slab per pair
+    assert lib.oo_pair_slab_list(8, 4, 5, None, 0) < 0
+    M, t0, mloc = 12, 5, 4
+    g = synthetic.eri_spatial_shard(M, t0, mloc)
+    packed = synthetic.eri_spatial_pair_packed(M, t0, mloc)
+    ref = torch.stack([g[t - t0, q] for t, q in distributed.pair_slab_list(M, t0, mloc)])
+    assert torch.equal(packed, ref)
