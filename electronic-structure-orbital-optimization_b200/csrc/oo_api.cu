@@ -552,6 +552,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   // A blocking stream: it orders itself against the legacy default stream, which is where a host
   // framework (torch) produces the input tensors unless told otherwise.
   if (e == cudaSuccess) e = cudaStreamCreate(&c->stream);
+  c->own_stream = (e == cudaSuccess && c->stream != nullptr);   // so that a failed create frees it
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -563,7 +564,6 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     oo_destroy(c);
     return rc;
   }
-  c->own_stream = true;
   *out = c;
   return OO_OK;
 }

@@ -1,0 +1,136 @@
+"""Inner-loop timing at the reference's own problem sizes (BASELINE.json configs 1-3).
+
+For each config the SAME spin-orbital tensors (the reference's (2M)^4 layout) go
+  (a) through the drop-in optimiser, esoo_b200.PartialUnitaryProjectionOptimizer(device='cuda'),
+      called exactly like the reference class: first call (ingest + engine creation) and a second
+      call on re-created device tensors (what the outer loop does every iteration: the engine
+      cache recognises the integrals);
+  (b) through the reference's formulation on the host cores (oracle/torch_port.py: block_diag,
+      the reference's einsum strings, autograd), one optimiser iteration = energy-only forward +
+      forward/backward, as in partial_unitary_projection_optimizer.py:304-346.
+Real-molecule integrals need pyscf, so the tensors are the seeded synthetic ones of the same
+M, N.  One JSON line per config.
+
+    python examples/reference_configs_timing.py [--iters 300] [--configs 1,2,3]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import esoo_b200  # noqa: E402
+from esoo_b200 import synthetic  # noqa: E402
+from oracle import torch_port  # noqa: E402  (bench baseline leg: the checker, never the product)
+
+CONFIGS = {
+    1: ("cfg1: H2 cc-pVTZ shape", 28, 2, 1, None),
+    2: ("cfg2: H4 cc-pVTZ shape", 56, 4, 1, None),
+    3: ("cfg3: H2 cc-pV5Z shape, 3 states", 110, 2, 3, [3, 2, 1]),
+}
+
+
+class _Solver:
+    """What the optimiser reads from the bound objective (name, weight_vector)."""
+    wavefunction_real = True
+
+    def __init__(self, weights):
+        if weights is not None:
+            self.weight_vector = list(weights)
+
+    def compute_rotated_energy(self, *a, **k):
+        raise AssertionError("not called by the CUDA optimiser")
+
+    def compute_rotated_weighted_energy_sum(self, *a, **k):
+        raise AssertionError("not called by the CUDA optimiser")
+
+
+def host_ram_gb():
+    with open("/proc/meminfo") as f:
+        for line in f:
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    return 0.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--configs", default="1,2,3")
+    ap.add_argument("--cpu-repeats", type=int, default=2)
+    args = ap.parse_args()
+    dev = "cuda:0"
+    for cid in [int(x) for x in args.configs.split(",")]:
+        name, M, N, k, weights = CONFIGS[cid]
+        spin_bytes = (2 * M) ** 4 * 8
+        if host_ram_gb() < 3.5 * spin_bytes / 1e9 + 8:
+            print(json.dumps({"config": name, "skipped": f"host RAM {host_ram_gb():.0f} GB"}))
+            continue
+        h, g = synthetic.h_spatial(M), synthetic.eri_spatial(M)
+        hs, gs = synthetic.spin_orbital_integrals(h, g, "abba")
+        del g
+        rd = [synthetic.rdms_spin(N, seed=synthetic.SEED_RDM + n) for n in range(k)]
+        Ds, Gs = [d for d, _ in rd], [g2 for _, g2 in rd]
+        U0 = synthetic.random_partial_unitary(M, N)
+        solver = _Solver(weights)
+        fun = solver.compute_rotated_energy if k == 1 else solver.compute_rotated_weighted_energy_sum
+        one, two = (Ds[0], Gs[0]) if k == 1 else (Ds, Gs)
+        to = (lambda t: [x.to(dev) for x in t] if isinstance(t, list) else t.to(dev))
+
+        timings, iters = [], []
+        for call in range(2):                       # cold, then warm (engine cache hit)
+            calls = []
+            opt = esoo_b200.PartialUnitaryProjectionOptimizer(
+                1e-3, 0.0, args.iters, callback=lambda it, e: calls.append(e), device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            # the reference's outer loop moves everything to the device right before the call
+            # (opt_orb_minimum_eigensolver.py:219-222) -- included in the timed region
+            U, E = opt.compute_optimal_rotation(fun=fun, initial_partial_unitary=U0.clone(),
+                                                oneRDM=to(one), twoRDM=to(two),
+                                                one_body_integrals=hs.to(dev),
+                                                two_body_integrals=gs.to(dev))
+            torch.cuda.synchronize()
+            timings.append(time.perf_counter() - t0)
+            iters.append(len(calls))
+        # the same loop with everything already resident (what the device loop itself costs)
+        eng = opt._prepare(fun, to(one), to(two), hs.to(dev), gs.to(dev), N)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = eng.optimize(U0.numpy(), 1e-3, 0.0, args.iters)
+        t_dev = time.perf_counter() - t0
+
+        # host: the reference's formulation, per optimiser iteration
+        w = weights if weights is not None else [1.0]
+        t_eval, t_iter, E_cpu, grad_cpu = torch_port.time_reference_spin(
+            U0, Ds, Gs, w, hs, gs, repeats=args.cpu_repeats)
+        E_gpu, grad_gpu = eng.energy_grad(U0)
+        dE = abs(float(E_gpu) - E_cpu)
+        dg = float((grad_gpu.cpu() - grad_cpu).norm() / grad_cpu.norm())
+        line = {
+            "config": name, "M": M, "N": N, "states": k,
+            "spin_orbital_g_bytes": spin_bytes,
+            "gpu_first_call_s": timings[0], "gpu_second_call_s": timings[1],
+            "iterations_per_call": iters[1],
+            "gpu_iterations_per_s_second_call": iters[1] / timings[1],
+            "gpu_iterations_per_s_resident": res["n_iter"] / t_dev,
+            "cpu_reference_formulation_s_per_iteration": t_iter,
+            "cpu_reference_formulation_iterations_per_s": 1.0 / t_iter,
+            "cpu_threads": torch.get_num_threads(),
+            "speedup_second_call": (iters[1] / timings[1]) * t_iter,
+            "speedup_resident": (res["n_iter"] / t_dev) * t_iter,
+            "parity_dE": dE, "parity_rel_grad": dg,
+            "final_energy": float(E),
+        }
+        print(json.dumps(line), flush=True)
+        esoo_b200.clear_engine_cache()
+        del hs, gs, eng, opt
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,3 +52,38 @@ def time_reference(U, D, G, h, g_slab, s0: int = 0, repeats: int = 1):
         t_eval += c - b
         t_iter += c - a
     return t_eval / repeats, t_iter / repeats
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's formulation on its own (spin-orbital) tensors: W = block_diag(U, U)
+# (base_opt_orb_solver.py:549), the two einsum strings of :554-563, the state-weighted sum of
+# opt_orb_eigensolver.py:156-169 and autograd through all of it.  Used to time the reference's
+# real problem sizes (BASELINE.json configs 1-3) on the host cores.
+# ------------------------------------------------------------------------------------------------
+def energy_spin(U, oneRDMs, twoRDMs, weights, h_spin, g_spin):
+    W = torch.block_diag(U, U)
+    total = 0
+    for w, D, G in zip(weights, oneRDMs, twoRDMs):
+        e = torch.einsum('pq,pi,qj,ij', h_spin, W, W, D)
+        e = e + torch.einsum('pqrs,pi,qj,rk,sl,ijkl', g_spin, W, W, W, W, G)
+        total = total + float(w) * e
+    return total
+
+
+def time_reference_spin(U, oneRDMs, twoRDMs, weights, h_spin, g_spin, repeats: int = 1):
+    """(seconds per (E, dE/dU), seconds per reference optimiser iteration, E, grad) for the
+    spin-orbital problem, every state evaluated in turn as the reference does."""
+    t_eval = t_iter = 0.0
+    E = grad = None
+    for _ in range(repeats):
+        a = time.perf_counter()
+        with torch.no_grad():
+            energy_spin(U, oneRDMs, twoRDMs, weights, h_spin, g_spin)      # pupo.py:310
+        b = time.perf_counter()
+        Ur = U.clone().requires_grad_(True)
+        E = energy_spin(Ur, oneRDMs, twoRDMs, weights, h_spin, g_spin)     # pupo.py:85-103
+        (grad,) = torch.autograd.grad([E], inputs=[Ur])
+        c = time.perf_counter()
+        t_eval += c - b
+        t_iter += c - a
+    return t_eval / repeats, t_iter / repeats, float(E.detach()), grad
