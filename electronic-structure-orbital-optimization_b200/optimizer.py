@@ -16,7 +16,11 @@ Differences, all deliberate:
   * user callbacks are delivered in order and with the reference's arguments while the device
     loop runs, at most one chunk (4 iterations) late (same (iteration, energy) pairs);
   * instances hold no device handles, so `copy.deepcopy` (base_opt_orb_solver.py:75) is safe;
-    engines are cached in a module-level registry keyed by the integral tensors.
+    engines are cached in a module-level registry keyed by the integral tensors;
+  * `inputs_on_host=True` (extension) makes `.device` report 'cpu' while the work still runs on
+    the CUDA device: the outer loops move h, g and the RDMs to `optimizer.device` before every
+    call (opt_orb_minimum_eigensolver.py:219-222), which for an 18.7 GB (2M)^4 tensor costs far
+    more than the optimisation itself; with host inputs a cache hit touches 1 % of the tensor.
 """
 from __future__ import annotations
 
@@ -66,7 +70,8 @@ class PartialUnitaryProjectionOptimizer:
                  callback: Optional[Callable] = None,
                  decay_factor: float = 0.8,
                  gradient_method: Optional[str] = 'autograd',
-                 device: Optional[str] = 'cuda') -> None:
+                 device: Optional[str] = 'cuda',
+                 inputs_on_host: bool = False) -> None:
         if gradient_method not in ('autograd', 'finite_difference'):
             raise ValueError("gradient_method must be 'autograd' or 'finite_difference'")
         if not str(device).startswith('cuda'):
@@ -77,7 +82,9 @@ class PartialUnitaryProjectionOptimizer:
         self.maxiter = maxiter
         self._BBstepsize = initial_BBstepsize
         self.decay_factor = decay_factor
-        self.device = device
+        self.compute_device = device
+        # what the outer loops read to decide where to put the tensors they pass in
+        self.device = 'cpu' if inputs_on_host else device
         self.gradient_method = gradient_method
         self.last_result = None      # bookkeeping of the most recent compute_optimal_rotation
 
@@ -100,7 +107,7 @@ class PartialUnitaryProjectionOptimizer:
 
     # -- engine plumbing -----------------------------------------------------------------------
     def _torch_device(self) -> torch.device:
-        d = torch.device(self.device)
+        d = torch.device(self.compute_device)
         return torch.device('cuda', d.index if d.index is not None else torch.cuda.current_device())
 
     def _engine_for(self, one_body_integrals: torch.Tensor, two_body_integrals: torch.Tensor):

@@ -656,3 +656,29 @@ def test_pair_packed_storage_is_bit_identical(torch_cuda, M, N, t0, mloc):
         assert float(E2) == float(E0) and torch.equal(g2, g0)
     eng.close()
     dense.close()
+
+
+def test_inputs_on_host_option(torch_cuda):
+    """inputs_on_host=True: `.device` reads 'cpu', so the outer loop hands over host tensors (no
+    per-iteration H2D of the (2M)^4 tensor); the result is the same as with device inputs."""
+    import esoo_b200
+    from esoo_b200 import harness
+    torch = torch_cuda
+    gold = load_golden("outer_H4_631G_ground")
+    hs, gs = torch.from_numpy(gold["h_spin"]), torch.from_numpy(gold["g_spin"])
+    N = int(gold["N"])
+    runs = []
+    for on_host in (False, True):
+        esoo_b200.clear_engine_cache()
+        opt = esoo_b200.PartialUnitaryProjectionOptimizer(float(gold["bb0"]), float(gold["tol"]),
+                                                          int(gold["maxiter"]), device="cuda:0",
+                                                          inputs_on_host=on_host)
+        assert opt.device == ("cpu" if on_host else "cuda:0") and opt.compute_device == "cuda:0"
+        res = harness.run_outer_loop(opt, hs, gs, 2 * N, int(gold["n_alpha"]), int(gold["n_beta"]),
+                                     maxiter=int(gold["outer_maxiter"]),
+                                     stopping_tolerance=float(gold["outer_tol"]))
+        runs.append(np.array(res["energies"]))
+        assert res["U"].device.type == "cpu"
+    assert np.array_equal(runs[0], runs[1])
+    assert np.max(np.abs(runs[1] - gold["energies"])) <= EFINAL_TOL
+    esoo_b200.clear_engine_cache()

@@ -55,8 +55,14 @@ def test_constructor_mirrors_reference_signature():
     import inspect
     import esoo_b200
     sig = inspect.signature(esoo_b200.PartialUnitaryProjectionOptimizer.__init__)
-    assert list(sig.parameters)[1:] == ["initial_BBstepsize", "stopping_tolerance", "maxiter",
-                                        "callback", "decay_factor", "gradient_method", "device"]
+    # the reference's parameters in the reference's order; extensions only after them
+    assert list(sig.parameters)[1:8] == ["initial_BBstepsize", "stopping_tolerance", "maxiter",
+                                         "callback", "decay_factor", "gradient_method", "device"]
+    assert list(sig.parameters)[8:] == ["inputs_on_host"]
+    assert sig.parameters["inputs_on_host"].default is False
+    oh = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 7, device="cuda:1",
+                                                     inputs_on_host=True)
+    assert oh.device == "cpu" and oh.compute_device == "cuda:1"
     o = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 7, device="cuda:1")
     assert (o.BBstepsize, o.stopping_tolerance, o.maxiter, o.decay_factor, o.device,
             o.gradient_method, o.callback) == (0.1, 1e-6, 7, 0.8, "cuda:1", "autograd", None)
@@ -83,8 +89,12 @@ def test_signature_matches_live_reference():
     for name in ("__init__", "orth", "compute_rotated_energy_automatic_gradient",
                  "compute_rotated_energy_gradient", "compute_updated_partial_unitary",
                  "compute_optimal_rotation"):
-        assert list(inspect.signature(getattr(ours, name)).parameters) == \
-            list(inspect.signature(getattr(Ref, name)).parameters), name
+        mine = list(inspect.signature(getattr(ours, name)).parameters)
+        theirs = list(inspect.signature(getattr(Ref, name)).parameters)
+        if name == "__init__":                      # extensions may follow the reference's list
+            assert mine[:len(theirs)] == theirs and mine[len(theirs):] == ["inputs_on_host"]
+        else:
+            assert mine == theirs, name
 
 
 def test_fun_identification():
