@@ -33,7 +33,7 @@ constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
 constexpr int K1_THREADS = (K1_NWARP + 2) * 32;    // + 1 TMA producer warp + 1 epilogue warp
 constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
 constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
-constexpr int K1_BAR_FOLD = 3;                     // named barrier: consumers only, between fold rounds
+constexpr int K1_BAR_FOLD = 3;                     // first of the two-warp hand-over barriers (ids 3..12)
 constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + epilogue warp
 
 struct K1Params {
@@ -84,19 +84,6 @@ __device__ __forceinline__ void k1_mma_chunk_n(double (&acc)[K1_RB][NT][2], cons
         dmma884(acc[rb][nt][0], acc[rb][nt][1], f.u[nt][j], f.g[rb][j]);
 }
 
-template <int NT>
-__device__ __forceinline__ void k1_mma_chunk(double (&acc)[K1_RB][NT][2], const K1Frag<NT>& f,
-                                             int nact) {
-  static_assert(K1_RB == 4, "switch below enumerates 0..4 active row-blocks");
-  switch (nact) {
-    case 4: k1_mma_chunk_n<NT, 4>(acc, f); break;
-    case 3: k1_mma_chunk_n<NT, 3>(acc, f); break;
-    case 2: k1_mma_chunk_n<NT, 2>(acc, f); break;
-    case 1: k1_mma_chunk_n<NT, 1>(acc, f); break;
-    default: break;
-  }
-}
-
 // End of a pass: Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over the warp's NACT row-blocks, then
 // clear the Z^T accumulators.
 template <int NT, int NACT>
@@ -106,16 +93,21 @@ __device__ __forceinline__ void k1_second_gemm_n(double (&yacc)[NT][NT][2],
 #pragma unroll
   for (int rb = 0; rb < NACT; ++rb) {
     const uint32_t ub = ub0 + (uint32_t)(rb * K1_NWARP * 8 * 8);  // 8 rows per block, NWARP apart
+    // all B fragments of the row-block first, then the DMMAs ordered so that two updates of the
+    // same accumulator are NT*NT issues apart (back-to-back dependent DMMAs stall on the result)
+    double b[NT][2];
 #pragma unroll
     for (int nk = 0; nk < NT; ++nk) {
-      const double b0 = lds64(ub + nk * u_nt_stride);       // U[row0 + c    ][nk*8+g]
-      const double b1 = lds64(ub + nk * u_nt_stride + 32);  // U[row0 + c + 4][nk*8+g]
-#pragma unroll
-      for (int nl = 0; nl < NT; ++nl) {
-        dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][0], b0);
-        dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][1], b1);
-      }
+      b[nk][0] = lds64(ub + nk * u_nt_stride);       // U[row0 + c    ][nk*8+g]
+      b[nk][1] = lds64(ub + nk * u_nt_stride + 32);  // U[row0 + c + 4][nk*8+g]
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int nk = 0; nk < NT; ++nk)
+#pragma unroll
+        for (int nl = 0; nl < NT; ++nl)
+          dmma884(yacc[nl][nk][0], yacc[nl][nk][1], acc[rb][nl][j], b[nk][j]);
   }
 #pragma unroll
   for (int rb = 0; rb < K1_RB; ++rb)
@@ -123,17 +115,67 @@ __device__ __forceinline__ void k1_second_gemm_n(double (&yacc)[NT][NT][2],
     for (int nt = 0; nt < NT; ++nt) acc[rb][nt][0] = acc[rb][nt][1] = 0.0;
 }
 
+// Ring position and per-lane shared-memory addresses of one consumer warp.
+struct K1Cons {
+  uint32_t g_addr[2];   // this lane's 16 B of row-block `warp` in stage 0, k8 halves 0 / 1
+  uint32_t u_addr;      // this lane's A fragment of U^T at column 0
+  uint32_t u_nt_stride; // bytes between column tiles of U^T
+  uint32_t full_base, empty_base;
+  int stage, nstage;
+  uint32_t phase;
+};
+
 template <int NT>
-__device__ __forceinline__ void k1_second_gemm(double (&yacc)[NT][NT][2],
-                                               double (&acc)[K1_RB][NT][2], uint32_t ub0,
-                                               uint32_t u_nt_stride, int nact) {
-  switch (nact) {
-    case 4: k1_second_gemm_n<NT, 4>(yacc, acc, ub0, u_nt_stride); break;
-    case 3: k1_second_gemm_n<NT, 3>(yacc, acc, ub0, u_nt_stride); break;
-    case 2: k1_second_gemm_n<NT, 2>(yacc, acc, ub0, u_nt_stride); break;
-    case 1: k1_second_gemm_n<NT, 1>(yacc, acc, ub0, u_nt_stride); break;
-    default: k1_second_gemm_n<NT, 0>(yacc, acc, ub0, u_nt_stride); break;
+__device__ __forceinline__ void k1_load_frag(K1Frag<NT>& f, const K1Cons& s, int stage,
+                                             uint32_t ucol, int half) {
+  const uint32_t sb = s.g_addr[half] + (uint32_t)stage * K1_STAGE_BYTES;
+#pragma unroll
+  for (int rb = 0; rb < K1_RB; ++rb)
+    lds128(f.g[rb][0], f.g[rb][1], sb + (uint32_t)(rb * K1_NWARP * 1024));
+  const uint32_t ub = s.u_addr + ucol + (uint32_t)(half * 64);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) lds128(f.u[nt][0], f.u[nt][1], ub + nt * s.u_nt_stride);
+}
+
+// One 256-row pass over a slab: nkc chunks of 16 columns through the TMA ring, then GEMM 2.
+// NACT (this warp's row-blocks inside the slab in this pass) is a template parameter selected
+// once per pass: a predicated-off DMMA still occupies the tensor pipe (measured:
+// profiles/r01_ncu_summary.md) and a per-chunk switch costs an indirect branch per 24 DMMAs.
+// f0 holds the first k8 half of the next chunk on entry and on exit (software pipeline across
+// pass and slab boundaries); `last` = nothing follows this pass.
+template <int NT, int NACT>
+__device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&yacc)[NT][NT][2],
+                                        K1Frag<NT>& f0, K1Frag<NT>& f1, K1Cons& s, int nkc,
+                                        bool last, uint32_t ub2, int lane) {
+  uint32_t ucol = 0;   // byte offset of the chunk's first column inside a row of U^T
+  for (int kc = 0; kc < nkc; ++kc) {
+    k1_load_frag<NT>(f1, s, s.stage, ucol, 1);
+    k1_mma_chunk_n<NT, NACT>(acc, f0);
+
+    int ns = s.stage + 1;
+    uint32_t nph = s.phase;
+    if (ns == s.nstage) {
+      ns = 0;
+      nph ^= 1u;
+    }
+    const bool wrap = kc + 1 == nkc;
+    const uint32_t nucol = wrap ? 0u : ucol + (uint32_t)(K1_KC * 8);
+    if (!(wrap && last)) {
+      mbar_wait(s.full_base + 8u * ns, nph);
+      k1_load_frag<NT>(f0, s, ns, nucol, 0);
+    }
+
+    k1_mma_chunk_n<NT, NACT>(acc, f1);
+
+    // All shared-memory reads of the stage are complete (their values fed the MMAs above).
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s.empty_base + 8u * s.stage);
+    s.stage = ns;
+    s.phase = nph;
+    ucol = nucol;
   }
+  // Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over this warp's rows of the pass
+  k1_second_gemm_n<NT, NACT>(yacc, acc, ub2, s.u_nt_stride);
 }
 
 // 10 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
@@ -183,7 +225,6 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   const int nrb_total = (p.M + 7) / 8;
   int nmine = 0;
   if ((int)blockIdx.x < p.nslab) nmine = (p.nslab - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
-  const long total_chunks = (long)nmine * npass * nkc;
 
   if (warp == K1_NWARP) {
     // ------------------------------ TMA producer ------------------------------
@@ -239,15 +280,20 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   const int rho = (g >> 1) | ((g & 1) << 2);
   // Byte offset of this lane's 16 B (two doubles: columns 2c, 2c+1 of the k8 half) inside an
   // 8-row block of a swizzled stage; half h in {0,1} selects columns [8h, 8h+8).
-  uint32_t goff[2];
-  goff[0] = (uint32_t)(rho * 128 + (((0 * 4 + c) ^ rho) << 4));
-  goff[1] = (uint32_t)(rho * 128 + (((1 * 4 + c) ^ rho) << 4));
+  K1Cons cs;
+  cs.g_addr[0] = stage_base + (uint32_t)(warp * 1024 + rho * 128 + (((0 * 4 + c) ^ rho) << 4));
+  cs.g_addr[1] = stage_base + (uint32_t)(warp * 1024 + rho * 128 + (((1 * 4 + c) ^ rho) << 4));
   const uint32_t ut_base = smem_u32(Ut);
   // A operand for GEMM 1: lane reads Ut[nt*8+g][col + 2c .. 2c+1]
-  const uint32_t uoff_a = (uint32_t)((g * p.upitch + 2 * c) * 8);
+  cs.u_addr = ut_base + (uint32_t)((g * p.upitch + 2 * c) * 8);
   // B operand for GEMM 2: lane reads Ut[nt*8+g][row + c] and [row + c + 4]
-  const uint32_t uoff_b = (uint32_t)((g * p.upitch + c) * 8);
-  const uint32_t u_nt_stride = (uint32_t)(8 * p.upitch * 8);
+  const uint32_t u_addr_b = ut_base + (uint32_t)((g * p.upitch + c + warp * 8) * 8);
+  cs.u_nt_stride = (uint32_t)(8 * p.upitch * 8);
+  cs.full_base = full_base;
+  cs.empty_base = empty_base;
+  cs.stage = 0;
+  cs.nstage = p.nstage;
+  cs.phase = 0;
 
   double acc[K1_RB][NT][2];   // Z^T fragments of the current pass
   double yacc[NT][NT][2];     // Y^T fragments of the current slab
@@ -260,104 +306,53 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
 #pragma unroll
     for (int b = 0; b < NT; ++b) yacc[a][b][0] = yacc[a][b][1] = 0.0;
 
-  auto load_frag = [&](K1Frag<NT>& f, int stage, int kc, int half) {
-    const uint32_t sb = stage_base + (uint32_t)stage * K1_STAGE_BYTES + goff[half];
-#pragma unroll
-    for (int rb = 0; rb < K1_RB; ++rb)
-      lds128(f.g[rb][0], f.g[rb][1], sb + (uint32_t)((rb * K1_NWARP + warp) * 1024));
-    const uint32_t ub = ut_base + uoff_a + (uint32_t)((kc * K1_KC + half * 8) * 8);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) lds128(f.u[nt][0], f.u[nt][1], ub + nt * u_nt_stride);
-  };
-
-  int stage = 0;
-  uint32_t phase = 0;
-  int slab = blockIdx.x, pass = 0, kc = 0;
-  int nrb_pass = min(K1_NWARP * K1_RB, nrb_total);  // active row-blocks in the current pass
-
   K1Frag<NT> f0, f1;
-  if (total_chunks > 0) {
+  if (nmine > 0) {
     mbar_wait(full_base, 0);
-    load_frag(f0, 0, 0, 0);
+    k1_load_frag<NT>(f0, cs, 0, 0u, 0);
   }
 
-  for (long ci = 0; ci < total_chunks; ++ci) {
-    // this warp's row-blocks rb*NWARP+warp < nrb_pass form a prefix of length nact (0..RB)
-    const int nact = max(0, min(K1_RB, (nrb_pass - warp + K1_NWARP - 1) / K1_NWARP));
-
-    load_frag(f1, stage, kc, 1);
-    k1_mma_chunk<NT>(acc, f0, nact);
-
-    // Prefetch the first half of the next chunk (next stage of the ring).
-    int nstage_i = stage + 1;
-    uint32_t nphase = phase;
-    if (nstage_i == p.nstage) {
-      nstage_i = 0;
-      nphase ^= 1u;
-    }
-    int nkc_i = kc + 1, npass_i = pass, nslab_i = slab;
-    if (nkc_i == nkc) {
-      nkc_i = 0;
-      if (++npass_i == npass) {
-        npass_i = 0;
-        nslab_i += gridDim.x;
+  static_assert(K1_RB == 4, "the switch below enumerates 0..4 active row-blocks");
+  for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+    const bool last_slab = slab + (int)gridDim.x >= p.nslab;
+    for (int pass = 0; pass < npass; ++pass) {
+      // this warp's row-blocks rb*NWARP+warp inside the slab form a prefix of length nact (0..RB)
+      const int nrb_pass = min(K1_NWARP * K1_RB, nrb_total - pass * K1_NWARP * K1_RB);
+      const int nact = max(0, min(K1_RB, (nrb_pass - warp + K1_NWARP - 1) / K1_NWARP));
+      const bool last = last_slab && pass == npass - 1;
+      const uint32_t ub2 = u_addr_b + (uint32_t)(pass * K1_ROWS * 8);
+      switch (nact) {
+        case 4: k1_pass<NT, 4>(acc, yacc, f0, f1, cs, nkc, last, ub2, lane); break;
+        case 3: k1_pass<NT, 3>(acc, yacc, f0, f1, cs, nkc, last, ub2, lane); break;
+        case 2: k1_pass<NT, 2>(acc, yacc, f0, f1, cs, nkc, last, ub2, lane); break;
+        case 1: k1_pass<NT, 1>(acc, yacc, f0, f1, cs, nkc, last, ub2, lane); break;
+        default: k1_pass<NT, 0>(acc, yacc, f0, f1, cs, nkc, last, ub2, lane); break;
       }
     }
-    if (ci + 1 < total_chunks) {
-      mbar_wait(full_base + 8u * nstage_i, nphase);
-      load_frag(f0, nstage_i, nkc_i, 0);
-    }
-
-    k1_mma_chunk<NT>(acc, f1, nact);
-
-    // All shared-memory reads of `stage` are complete (their values fed the MMAs above).
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_base + 8u * stage);
-
-    if (kc == nkc - 1) {
-      // ---- end of pass: Y^T[l][k] += sum_r Z^T[l][r] * U[r][k] over this warp's rows ----
-      k1_second_gemm<NT>(yacc, acc,
-                         ut_base + uoff_b + (uint32_t)((pass * K1_ROWS + warp * 8) * 8),
-                         u_nt_stride, nact);
-      if (pass == npass - 1) {
-        // ---- end of slab: hand the per-warp partial tile to the epilogue warp ----
-        named_bar_sync(K1_BAR_FREE, K1_BAR_COUNT);   // previous slab's tile has been consumed
-        // warps w, w+npart, w+2*npart, ... share buffer w % npart; they are folded in rounds
-        // (fixed order => deterministic), separated by a consumer-only barrier
-        double* mine = Ypart + (warp % p.npart) * Np * Np;
-        const int rounds = K1_NWARP / p.npart;
-        for (int rnd = 0; rnd < rounds; ++rnd) {
-          if (warp / p.npart == rnd) {
+    // ---- end of slab: hand the per-warp partial tile to the epilogue warp ----
+    named_bar_sync(K1_BAR_FREE, K1_BAR_COUNT);   // previous slab's tile has been consumed
+    // warps w, w+npart, w+2*npart, ... share buffer w % npart and add their tiles to it one
+    // after the other (fixed order => deterministic).  Each hand-over is a two-warp
+    // arrive/sync pair on its own named barrier, so nobody else waits.
+    const int buf = warp % p.npart, turn = warp / p.npart;
+    double* mine = Ypart + buf * Np * Np;
+    if (turn > 0) named_bar_sync(K1_BAR_FOLD + buf * 3 + (turn - 1), 64);
 #pragma unroll
-            for (int nl = 0; nl < NT; ++nl)
+    for (int nl = 0; nl < NT; ++nl)
 #pragma unroll
-              for (int nk = 0; nk < NT; ++nk) {
-                double2* dst =
-                    reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c);
-                double2 v = make_double2(yacc[nl][nk][0], yacc[nl][nk][1]);
-                if (rnd > 0) {
-                  const double2 o = *dst;
-                  v.x += o.x;
-                  v.y += o.y;
-                }
-                *dst = v;
-                yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
-              }
-          }
-          if (rnd + 1 < rounds) named_bar_sync(K1_BAR_FOLD, K1_NWARP * 32);
+      for (int nk = 0; nk < NT; ++nk) {
+        double2* dst = reinterpret_cast<double2*>(mine + (nl * 8 + g) * Np + nk * 8 + 2 * c);
+        double2 v = make_double2(yacc[nl][nk][0], yacc[nl][nk][1]);
+        if (turn > 0) {
+          const double2 o = *dst;
+          v.x += o.x;
+          v.y += o.y;
         }
-        named_bar_arrive(K1_BAR_FULL, K1_BAR_COUNT);
+        *dst = v;
+        yacc[nl][nk][0] = yacc[nl][nk][1] = 0.0;
       }
-    }
-
-    stage = nstage_i;
-    phase = nphase;
-    kc = nkc_i;
-    if (npass_i != pass || nslab_i != slab) {
-      pass = npass_i;
-      slab = nslab_i;
-      nrb_pass = min(K1_NWARP * K1_RB, nrb_total - pass * K1_NWARP * K1_RB);
-    }
+    if ((turn + 1) * p.npart < K1_NWARP) named_bar_arrive(K1_BAR_FOLD + buf * 3 + turn, 64);
+    named_bar_arrive(K1_BAR_FULL, K1_BAR_COUNT);
   }
 }
 
