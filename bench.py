@@ -347,6 +347,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "k1_half_transform", "ms_per_launch": k1_avg,
+                         "ms_per_launch_median_rank0": sorted(k1_ms)[len(k1_ms) // 2],
+                         "ms_per_launch_min_rank0": min(k1_ms),
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "stream_read_gbs_measured_live": stream_read},
             "roofline_tensor": {"bound": "tensor", "achieved": ach_tf, "peak": dmma,
