@@ -182,7 +182,33 @@ def main_molecule():
                             U_final=res["U"].numpy(), e_nuc=mol["e_nuc"], e_hf=mol["e_hf"], **extra)
 
 
+# ------------------------------------------------------------------------------------------------
+# compute_updated_partial_unitary (pupo.py:129-159) called directly on the live reference:
+# iteration 0 keeps the step, odd / even iterations use the two Barzilai-Borwein formulas.
+# ------------------------------------------------------------------------------------------------
+def main_bb():
+    Pupo, _ = ref_loader.load_reference()
+    M, N, bb0 = 14, 3, 0.07
+    gen = torch.Generator().manual_seed(4242)
+    Uc = torch.linalg.qr(torch.randn(M, N, generator=gen, dtype=torch.float64))[0]
+    Up = torch.linalg.qr(torch.randn(M, N, generator=gen, dtype=torch.float64))[0]
+    Gc = torch.randn(M, N, generator=gen, dtype=torch.float64)
+    Gp = torch.randn(M, N, generator=gen, dtype=torch.float64)
+    out = {"M": M, "N": N, "bb0": bb0, "U_cur": Uc.numpy(), "U_prev": Up.numpy(),
+           "G_cur": Gc.numpy(), "G_prev": Gp.numpy(), "iterations": np.array([0, 1, 2, 5, 6])}
+    for it in out["iterations"]:
+        opt = Pupo(initial_BBstepsize=bb0, stopping_tolerance=1e-6, maxiter=10)
+        U_next = opt.compute_updated_partial_unitary(int(it), Uc.clone(), Up.clone(), Gc.clone(),
+                                                     Gp.clone())
+        out[f"U_next_{it}"] = U_next.numpy()
+        out[f"step_{it}"] = float(opt.BBstepsize)
+        print(f"bb_update iteration {it}: step {float(opt.BBstepsize):.12e}")
+    np.savez_compressed(os.path.join(HERE, "bb_update_M14_N3.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "bb":
+        main_bb()
     if len(sys.argv) < 2 or sys.argv[1] == "molecule":
         main_molecule()
     if len(sys.argv) < 2 or sys.argv[1] == "inner":

@@ -682,3 +682,20 @@ def test_inputs_on_host_option(torch_cuda):
     assert np.array_equal(runs[0], runs[1])
     assert np.max(np.abs(runs[1] - gold["energies"])) <= EFINAL_TOL
     esoo_b200.clear_engine_cache()
+
+
+def test_bb_update_vs_reference_golden(torch_cuda):
+    """oo_bb_update through the drop-in method against the live reference's
+    compute_updated_partial_unitary (fixture bb_update_M14_N3)."""
+    import esoo_b200
+    torch = torch_cuda
+    gold = load_golden("bb_update_M14_N3")
+    t = {k: torch.from_numpy(gold[k]) for k in ("U_cur", "U_prev", "G_cur", "G_prev")}
+    for it in gold["iterations"]:
+        opt = esoo_b200.PartialUnitaryProjectionOptimizer(float(gold["bb0"]), 1e-6, 10,
+                                                          device="cuda:0")
+        out = opt.compute_updated_partial_unitary(int(it), t["U_cur"], t["U_prev"], t["G_cur"],
+                                                  t["G_prev"])
+        assert np.max(np.abs(out.cpu().numpy() - gold[f"U_next_{it}"])) <= 1e-12
+        assert abs(float(opt.BBstepsize) - float(gold[f"step_{it}"])) <= \
+            1e-13 * abs(float(gold[f"step_{it}"]))

@@ -170,3 +170,14 @@ def test_oracle_outer_loop_on_molecule(name):
     assert np.max(np.abs(E - gold["energies"])) <= 1e-8
     if "ref_test_golden" in gold:
         assert np.max(np.abs(E[-1] - gold["ref_test_golden"])) < 2e-5
+
+
+def test_bb_update_vs_reference_golden():
+    """compute_updated_partial_unitary (pupo.py:129-159) of the live reference, iteration 0 / odd /
+    even: next iterate and the Barzilai-Borwein step it leaves in BBstepsize."""
+    gold = load_golden("bb_update_M14_N3")
+    for it in gold["iterations"]:
+        U_next, step = onp.bb_update(int(it), gold["U_cur"], gold["U_prev"], gold["G_cur"],
+                                     gold["G_prev"], float(gold["bb0"]))
+        assert abs(step - float(gold[f"step_{it}"])) <= 1e-13 * abs(step)
+        assert np.max(np.abs(U_next - gold[f"U_next_{it}"])) <= 1e-12
