@@ -206,7 +206,37 @@ def main_bb():
     np.savez_compressed(os.path.join(HERE, "bb_update_M14_N3.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# a non-default decay_factor changes the smoothed stopping measure (pupo.py:230,268,320) and hence
+# the iteration at which the loop stops
+# ------------------------------------------------------------------------------------------------
+def main_decay():
+    Pupo, _ = ref_loader.load_reference()
+    M, N = 6, 2
+    hs, gs, Ds, Gs, U0 = build_inputs(M, N, "abba", 1)
+    solver = ref_loader.make_solver(True, None)
+    out = {"M": M, "N": N, "pattern": "abba", "n_states": 1, "weights": np.array([1.0]),
+           "h_spin": hs.numpy(),
+           "g_spin": gs.numpy(), "D_spin_0": Ds[0].numpy(), "G_spin_0": Gs[0].numpy(),
+           "U0": U0.numpy(), "bb0": 0.05, "tol": 1e-7, "maxiter": 300,
+           "decays": np.array([0.2, 0.5, 0.95])}
+    for d in out["decays"]:
+        calls = []
+        opt = Pupo(initial_BBstepsize=0.05, stopping_tolerance=1e-7, maxiter=300,
+                   decay_factor=float(d), callback=lambda it, e: calls.append((it, e)))
+        U_fin, E_fin = opt.compute_optimal_rotation(
+            fun=solver.compute_rotated_energy, initial_partial_unitary=U0.clone(), oneRDM=Ds[0],
+            twoRDM=Gs[0], one_body_integrals=hs, two_body_integrals=gs)
+        out[f"E_{d}"] = float(E_fin)
+        out[f"U_{d}"] = U_fin.numpy()
+        out[f"calls_it_{d}"] = np.array([c[0] for c in calls], dtype=np.int64)
+        print(f"decay {d}: {len(calls)} callbacks, E = {float(E_fin):.12f}")
+    np.savez_compressed(os.path.join(HERE, "opt_decay_M6_N2.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "decay":
+        main_decay()
     if len(sys.argv) < 2 or sys.argv[1] == "bb":
         main_bb()
     if len(sys.argv) < 2 or sys.argv[1] == "molecule":

@@ -699,3 +699,24 @@ def test_bb_update_vs_reference_golden(torch_cuda):
         assert np.max(np.abs(out.cpu().numpy() - gold[f"U_next_{it}"])) <= 1e-12
         assert abs(float(opt.BBstepsize) - float(gold[f"step_{it}"])) <= \
             1e-13 * abs(float(gold[f"step_{it}"]))
+
+
+def test_decay_factor_vs_reference_golden(torch_cuda):
+    """decay_factor reaches the device-side stopping rule: same callback iterations and final
+    energy as the live reference for 0.2 / 0.5 / 0.95."""
+    import esoo_b200
+    gold = load_golden("opt_decay_M6_N2")
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    for d in gold["decays"]:
+        calls = []
+        opt = esoo_b200.PartialUnitaryProjectionOptimizer(
+            float(gold["bb0"]), float(gold["tol"]), int(gold["maxiter"]),
+            callback=lambda it, e: calls.append(it), decay_factor=float(d), device="cuda:0")
+        U, E = opt.compute_optimal_rotation(fun=_Solver().compute_rotated_energy,
+                                            initial_partial_unitary=U0.clone(), oneRDM=Ds[0],
+                                            twoRDM=Gs[0], one_body_integrals=hs,
+                                            two_body_integrals=gs)
+        assert calls == list(gold[f"calls_it_{d}"])
+        assert abs(float(E) - float(gold[f"E_{d}"])) <= EFINAL_TOL
+        assert np.max(np.abs(U.numpy() - gold[f"U_{d}"])) <= 1e-5
+    esoo_b200.clear_engine_cache()

@@ -181,3 +181,21 @@ def test_bb_update_vs_reference_golden():
                                      gold["G_prev"], float(gold["bb0"]))
         assert abs(step - float(gold[f"step_{it}"])) <= 1e-13 * abs(step)
         assert np.max(np.abs(U_next - gold[f"U_next_{it}"])) <= 1e-12
+
+
+def test_decay_factor_vs_reference_golden():
+    """Non-default decay_factor: the smoothed stopping measure (pupo.py:230,268,320) stops the
+    loop at a different iteration; the oracle follows the live reference for each value."""
+    gold = load_golden("opt_decay_M6_N2")
+    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+    D, G, h, g = Ds[0].numpy(), Gs[0].numpy(), hs.numpy(), gs.numpy()
+    counts = []
+    for d in gold["decays"]:
+        res = onp.optimal_rotation(lambda U: onp.rotated_energy_spin(U, D, G, h, g),
+                                   lambda U: onp.rotated_energy_grad_spin(U, D, G, h, g),
+                                   U0.numpy(), float(gold["bb0"]), float(gold["tol"]),
+                                   int(gold["maxiter"]), decay_factor=float(d))
+        assert [c[0] for c in res["callbacks"]] == list(gold[f"calls_it_{d}"])
+        assert abs(res["energy"] - float(gold[f"E_{d}"])) <= 1e-8
+        counts.append(len(res["callbacks"]))
+    assert len(set(counts)) == len(counts)         # the parameter really changes the stopping point
