@@ -179,7 +179,8 @@ __device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&ya
 }
 
 // 10 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
-// 65536 / 384 = 168 per thread; NT <= 2 needs ~142, NT = 3 fits, NT = 4 spills a little.
+// 65536 / 384 = 168 per thread (ptxas -v: NT = 1: 89, NT = 2: 125, NT = 3: 168 without spills,
+// NT = 4: 168 with ~0.9 KB of spills -- it still reaches 29 TFLOP/s).
 template <int NT>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
