@@ -219,6 +219,18 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
   p.npart = c->npart;
+  {
+    // L2 residency hints when the tiles written by this launch (Y + YT) are a small part of L2:
+    // the ERI stream is marked evict-first, the tiles evict-last, and the q-contraction that
+    // follows reads them from L2 instead of HBM (multi-GPU shards, small problems)
+    const size_t tile_bytes = (size_t)p.nslab * c->Np * c->Np * sizeof(double) * (pair ? 2 : 1);
+    // OO_L2_HINTS=<mask 0..3> overrides (experiments); OO_NO_L2_HINTS disables
+    static const char* env = getenv("OO_L2_HINTS");
+    static const bool off = getenv("OO_NO_L2_HINTS") != nullptr;
+    p.l2_hints = tile_bytes <= ((size_t)48 << 20) ? 3 : 0;
+    if (env && *env >= '0' && *env <= '3') p.l2_hints = *env - '0';
+    if (off) p.l2_hints = 0;
+  }
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[c->device & 7]) {
     CU_TRY(cudaFuncSetAttribute(k1_half_transform<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -49,6 +49,9 @@ struct K1Params {
   int nstage;            // TMA ring depth
   int Mk;                // M rounded up to a multiple of K1_KC
   int upitch;            // row pitch (doubles) of the transposed U copy in smem: Mk + 8
+  int l2_hints;          // bit 0: stream g with the L2 evict-first policy (it is read exactly once);
+                         // bit 1: store the Y / YT tiles evict-last so that the q-contraction finds
+                         // them in L2 (used when Y + YT are a small part of L2)
   int npart;             // partial-tile buffers at slab end: 8 (one per warp), 4 or 2 (warps are
                          // folded into them in fixed order; frees smem for one more TMA stage)
 };
@@ -230,6 +233,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   if (warp == K1_NWARP) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
       int stage = 0;
       uint32_t phase = 0;
       for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
@@ -238,8 +242,12 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(empty_base + 8u * stage, phase ^ 1u);
             mbar_arrive_expect_tx(full_base + 8u * stage, K1_STAGE_BYTES);
-            tma_load_3d(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
-                        pass * K1_ROWS, coord, full_base + 8u * stage);
+            if (p.l2_hints & 1)
+              tma_load_3d_hint(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
+                               pass * K1_ROWS, coord, full_base + 8u * stage, pol);
+            else
+              tma_load_3d(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
+                          pass * K1_ROWS, coord, full_base + 8u * stage);
             if (++stage == p.nstage) {
               stage = 0;
               phase ^= 1u;
@@ -257,6 +265,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     // partial tiles into shared memory and go on with the next slab; this warp sums the 8
     // partials in fixed order (deterministic) and stores the tile and its transpose.
     named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);           // the buffer starts out free
+    const uint64_t keep = l2_policy_evict_last();
     for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
       named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
       double* out = p.Y + (size_t)slab * Np * Np;
@@ -264,10 +273,15 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       for (int e = lane; e < Np * Np; e += 32) {
         double s = 0.0;
         for (int w = 0; w < p.npart; ++w) s += Ypart[w * Np * Np + e];
-        out[e] = s;
         // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
         // reads both orientations with unit stride
-        if (outT) outT[(e % Np) * Np + e / Np] = s;
+        if (p.l2_hints & 2) {
+          st_global_hint(out + e, s, keep);
+          if (outT) st_global_hint(outT + (e % Np) * Np + e / Np, s, keep);
+        } else {
+          out[e] = s;
+          if (outT) outT[(e % Np) * Np + e / Np] = s;
+        }
       }
       named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
     }
