@@ -20,6 +20,8 @@ SYMBOLS = [
     "oo_ingest_spin_g", "oo_set_rdms_spin", "oo_energy_grad_allreduce", "oo_peer_export",
     "oo_peer_attach", "oo_peer_status", "oo_set_integrals_generic",
     "oo_retraction_stats", "oo_set_callback", "oo_pair_slab_list", "oo_pack_pair_slabs",
+    "oo_eval_submit", "oo_eval_wait", "oo_request_stop", "oo_set_peer_timeout_ms",
+    "oo_ingest_spin_g_rows",
 ]
 
 OO_G_V4_SYMMETRIC = 1
@@ -79,6 +81,10 @@ def load() -> C.CDLL:
     lib.oo_energy_grad.argtypes = [vp, vp, vp]
     lib.oo_energy_grad_host.argtypes = [vp, vp, vp, vp]
     lib.oo_energy_grad_allreduce.argtypes = [vp, vp, vp]
+    lib.oo_eval_submit.argtypes = [vp, vp, C.c_int]
+    lib.oo_eval_wait.argtypes = [vp, C.c_int, vp, vp]
+    lib.oo_request_stop.argtypes = [vp]
+    lib.oo_set_peer_timeout_ms.argtypes = [vp, C.c_double]
     lib.oo_peer_export.argtypes = [vp, vp]
     lib.oo_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.oo_peer_status.argtypes = [vp]
@@ -102,6 +108,8 @@ def load() -> C.CDLL:
     lib.oo_pair_slab_list.argtypes = [C.c_int, C.c_int, C.c_int, ip, C.c_int]
     lib.oo_pack_pair_slabs.argtypes = [vp, vp, vp]
     lib.oo_ingest_spin_g.argtypes = [C.c_int, vp, C.c_int, C.c_double, vp, C.POINTER(C.c_uint), dp]
+    lib.oo_ingest_spin_g_rows.argtypes = [C.c_int, vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                          vp, C.POINTER(C.c_uint), dp]
     lib.oo_set_rdms_spin.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), dp, C.c_int, C.c_uint]
     for name in SYMBOLS:
         fn = getattr(lib, name)

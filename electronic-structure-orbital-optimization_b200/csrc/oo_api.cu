@@ -112,17 +112,16 @@ struct oo_ctx {
   bool generic = false;                // no V4 symmetry: two dense passes, four gradient slots
   bool packed = false;                 // g holds only the pair-selected slabs, in streaming order
   alignas(64) CUtensorMap tmap2;
-  double* Gp_slot[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* G2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // k_prepare_gamma2 kinds
+  double *QA = nullptr, *QB = nullptr, *Aslab = nullptr;   // fused evaluation (oo_k1.cuh)
+  bool step_fusable = true;            // OO_NO_STEP_FUSION=1: k_step stays a separate launch
   unsigned gflags = 0;
   bool have_ints = false, have_rdms = false;
   alignas(64) CUtensorMap tmap;
   // workspaces (device)
-  double *Y = nullptr, *T3 = nullptr, *Gp = nullptr, *D = nullptr, *A = nullptr, *UD = nullptr,
-         *UDt = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
+  double *Y = nullptr, *T3 = nullptr, *D = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
          *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr,
          *YT = nullptr, *Upad = nullptr, *B1 = nullptr, *B12 = nullptr, *Gtmp = nullptr;
-  cudaStream_t aux = nullptr;       // one-body terms run here, concurrently with K1
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int hist_cap = 0;
   unsigned int* counter = nullptr;
   // pair-symmetric slab selection (see oo_k2.cuh)
@@ -144,7 +143,20 @@ struct oo_ctx {
   bool peer_on = false;
   int peer_stride = 0;
   unsigned long long* peer_seq_dev = nullptr;
-  int* peer_err = nullptr;
+  int* peer_err = nullptr;              // device flag (sticky): a peer wait timed out
+  volatile int* peer_err_host = nullptr;   // the same flag in mapped host memory
+  int* peer_err_host_dev = nullptr;        // its device address
+  unsigned long long peer_timeout_ns = 20000000000ull;   // OO_PEER_TIMEOUT_MS / oo_set_peer_timeout_ms
+  // pipelined host-buffer evaluations (oo_eval_submit / oo_eval_wait): two slots
+  double* slot_pin_u[2] = {nullptr, nullptr};
+  double* slot_pin_out[2] = {nullptr, nullptr};
+  double* slot_u[2] = {nullptr, nullptr};
+  double* slot_out[2] = {nullptr, nullptr};
+  cudaEvent_t slot_h2d[2] = {nullptr, nullptr}, slot_eval[2] = {nullptr, nullptr},
+              slot_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  volatile int stop_requested = 0;      // oo_request_stop (from a callback)
   // CUDA graph of one chunk of optimiser transitions (oo_optimize)
   cudaGraphExec_t chunk_graph = nullptr;
   const void* graph_key[10] = {nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -202,14 +214,14 @@ int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map, size_t nslab
   return OO_OK;
 }
 
+// fused = true: the evaluation path (dot products with the Q tensors in the epilogue, Aslab out);
+// fused = false: tile mode (Y / YT out), used by oo_transform only.
 template <int NT>
-int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor) {
+int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor, bool fused) {
   K1Params p;
+  memset(&p, 0, sizeof p);
   p.U = U;
-  p.Y = c->Y;
   const bool pair = c->pair_sym && !c->generic;
-  p.YT = pair ? c->YT : nullptr;
-  p.Upad = c->Upad;
   p.done_flag = done_flag;
   p.M = c->M;
   p.N = c->N;
@@ -219,17 +231,22 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
   p.npart = c->npart;
-  {
-    // L2 residency hints when the tiles written by this launch (Y + YT) are a small part of L2:
-    // the ERI stream is marked evict-first, the tiles evict-last, and the q-contraction that
-    // follows reads them from L2 instead of HBM (multi-GPU shards, small problems)
-    const size_t tile_bytes = (size_t)p.nslab * c->Np * c->Np * sizeof(double) * (pair ? 2 : 1);
-    // OO_L2_HINTS=<mask 0..3> overrides (experiments); OO_NO_L2_HINTS disables
+  if (fused) {
+    p.QA = c->QA;
+    p.QB = (pair || c->generic) ? c->QB : nullptr;
+    p.Aslab = c->Aslab;
+    p.slab_tq = pair ? c->slab_coord : nullptr;
+    // the ERI stream is read exactly once: evict-first, so that the Q tensors (re-read by every
+    // slab) keep their place in L2.  OO_L2_HINTS=<mask> overrides (experiments).
     static const char* env = getenv("OO_L2_HINTS");
-    static const bool off = getenv("OO_NO_L2_HINTS") != nullptr;
-    p.l2_hints = tile_bytes <= ((size_t)48 << 20) ? 3 : 0;
+    p.l2_hints = 1;
     if (env && *env >= '0' && *env <= '3') p.l2_hints = *env - '0';
-    if (off) p.l2_hints = 0;
+  } else {
+    p.Y = c->Y;
+    p.YT = pair ? c->YT : nullptr;
+    p.Upad = c->Upad;
+    const size_t tile_bytes = (size_t)p.nslab * c->Np * c->Np * sizeof(double) * (pair ? 2 : 1);
+    p.l2_hints = tile_bytes <= ((size_t)48 << 20) ? 3 : 0;
   }
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[c->device & 7]) {
@@ -245,12 +262,52 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   return OO_OK;
 }
 
-int launch_k1(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor = false) {
+int launch_k1(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor, bool fused) {
   switch (c->NT) {
-    case 1: return launch_k1_t<1>(c, U, done_flag, second_tensor);
-    case 2: return launch_k1_t<2>(c, U, done_flag, second_tensor);
-    case 3: return launch_k1_t<3>(c, U, done_flag, second_tensor);
-    case 4: return launch_k1_t<4>(c, U, done_flag, second_tensor);
+    case 1: return launch_k1_t<1>(c, U, done_flag, second_tensor, fused);
+    case 2: return launch_k1_t<2>(c, U, done_flag, second_tensor, fused);
+    case 3: return launch_k1_t<3>(c, U, done_flag, second_tensor, fused);
+    case 4: return launch_k1_t<4>(c, U, done_flag, second_tensor, fused);
+  }
+  return fail(OO_ERR_INVALID, "unsupported N");
+}
+
+// Q tensors (QA for every orbital, QB for the shard's rows) and the one-body rows.
+template <int NT>
+int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB) {
+  constexpr int Np3 = NT * 8 * NT * 8 * NT * 8;
+  PrepParams pp;
+  pp.U = U;
+  pp.G2A = c->G2[kindA];
+  pp.G2B = kindB >= 0 ? c->G2[kindB] : nullptr;
+  pp.QA = c->QA;
+  pp.QB = c->QB;
+  pp.h = c->h;
+  pp.D = c->D;
+  pp.B1 = c->B1;
+  pp.B12 = c->B12;
+  pp.done_flag = done_flag;
+  pp.M = c->M;
+  pp.N = c->N;
+  pp.t0 = c->t0;
+  pp.mloc = c->mloc;
+  const int nbx = (Np3 + 255) / 256;
+  int chunks = std::max(1, std::min(c->M, (2 * c->num_sms + nbx - 1) / nbx));
+  chunks = std::max(chunks, (c->mloc + nbx - 1) / nbx);     // z = 2 needs nbx * chunks >= mloc CTAs
+  chunks = std::min(chunks, 65535);
+  pp.rows_per_chunk = (c->M + chunks - 1) / chunks;
+  k_prepare_q<NT><<<dim3(nbx, chunks, 3), 256, 0, c->stream>>>(pp);
+  CU_TRY(cudaGetLastError());
+  c->launches++;
+  return OO_OK;
+}
+
+int launch_prep(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB) {
+  switch (c->NT) {
+    case 1: return launch_prep_t<1>(c, U, done_flag, kindA, kindB);
+    case 2: return launch_prep_t<2>(c, U, done_flag, kindA, kindB);
+    case 3: return launch_prep_t<3>(c, U, done_flag, kindA, kindB);
+    case 4: return launch_prep_t<4>(c, U, done_flag, kindA, kindB);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -291,9 +348,9 @@ int launch_qc_t(oo_ctx* c, const int* done_flag, bool dense_mirror) {
 
 template <int NT>
 int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
-                  int slot) {
-  TailParams tp;
-  memset(&tp.comm, 0, sizeof tp.comm);
+                  int pass, const StepParams* step) {
+  TailReduceParams tp;
+  memset(&tp, 0, sizeof tp);
   if (fused) {
     tp.comm.enabled = 1;
     tp.comm.rank = c->rank;
@@ -301,13 +358,16 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
     tp.comm.stride = c->peer_stride;
     tp.comm.seq_ptr = c->peer_seq_dev;
     tp.comm.error_flag = c->peer_err;
+    tp.comm.error_flag_host = c->peer_err_host_dev;
+    tp.comm.timeout_ns = c->peer_timeout_ns;
     for (int r = 0; r < c->world; ++r) {
       tp.comm.flags[r] = (unsigned long long*)c->peer_map[r];
       tp.comm.slots[r] = (double*)((char*)c->peer_map[r] + 256);
     }
   }
-  tp.T3 = c->T3;
-  tp.Gp = slot < 0 ? c->Gp : c->Gp_slot[slot];
+  const bool pair = c->pair_sym && !c->generic;
+  tp.Aslab = c->Aslab;
+  tp.rowstart = pair ? c->rowstart : nullptr;
   tp.U = U;
   tp.B1 = c->B1;
   tp.B12 = c->B12;
@@ -319,26 +379,28 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.N = c->N;
   tp.t0 = c->t0;
   tp.mloc = c->mloc;
-  const bool pair = c->pair_sym && !c->generic;
-  tp.row0 = pair ? 0 : c->t0;
-  tp.nrows = pair ? c->M : c->mloc;
-  tp.two_body_grad_factor = slot < 0 ? 4.0 : 1.0;
-  tp.accumulate = slot > 0 ? 1 : 0;
-  constexpr int R = tail_rows(NT), AC = tail_ac(NT);
-  dim3 grid((tp.nrows + R - 1) / R, (NT * 8) / AC);
-  k_tail_row<NT><<<grid, TAIL_THREADS, 0, c->stream>>>(tp);
+  const bool all_rows = pair || c->generic;
+  tp.row0 = all_rows ? 0 : c->t0;
+  tp.nrows = all_rows ? c->M : c->mloc;
+  tp.mirror_mode = c->generic ? 2 : (pair ? 1 : 0);
+  tp.energy_mirror = c->generic ? 0 : 1;
+  tp.grad_factor = c->generic ? 1.0 : 4.0;
+  tp.accumulate = pass > 0 ? 1 : 0;
+  tp.do_step = step != nullptr ? 1 : 0;
+  if (step) tp.step = *step;
+  k_tail_reduce<NT><<<tp.nrows, TAIL_THREADS, 0, c->stream>>>(tp);
   CU_TRY(cudaGetLastError());
   c->launches++;
   return OO_OK;
 }
 
 int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
-                int slot = -1) {
+                int pass, const StepParams* step) {
   switch (c->NT) {
-    case 1: return launch_tail_t<1>(c, U, out, done_flag, fused, slot);
-    case 2: return launch_tail_t<2>(c, U, out, done_flag, fused, slot);
-    case 3: return launch_tail_t<3>(c, U, out, done_flag, fused, slot);
-    case 4: return launch_tail_t<4>(c, U, out, done_flag, fused, slot);
+    case 1: return launch_tail_t<1>(c, U, out, done_flag, fused, pass, step);
+    case 2: return launch_tail_t<2>(c, U, out, done_flag, fused, pass, step);
+    case 3: return launch_tail_t<3>(c, U, out, done_flag, fused, pass, step);
+    case 4: return launch_tail_t<4>(c, U, out, done_flag, fused, pass, step);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -353,78 +415,59 @@ int launch_qc(oo_ctx* c, const int* done_flag, bool dense_mirror = false) {
   return fail(OO_ERR_INVALID, "unsupported N");
 }
 
-// One evaluation: shard rows of dE/dU and partial E into `out` (device, M*N+1).
+// One evaluation: (partial) dE/dU and E into `out` (device, M*N+1).
 int do_allreduce(oo_ctx* c, double* buf, size_t count);
 
 // reduce = false: this GPU's partial only.  reduce = true: the sum over all GPUs, through the
 // all-reduce fused into the tail kernel (peer memory) when attached, else through NCCL.
-int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, bool reduce) {
+// step != NULL: the optimiser transition follows the evaluation (oo_optimize) -- inside the tail
+// kernel's last CTA when the reduced result is available there, else as a separate k_step launch.
+int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, bool reduce,
+                 const StepParams* step = nullptr) {
   if (!c->have_ints) return fail(OO_ERR_STATE, "oo_set_integrals has not been called");
   if (!c->have_rdms) return fail(OO_ERR_STATE, "oo_set_rdms has not been called");
   const bool tm = c->timing;
+  const bool pair = c->pair_sym && !c->generic;
+  const bool fused = reduce && c->peer_on && c->world > 1;
+  const bool nccl = reduce && !fused && c->world > 1;
+  const StepParams* step_in_tail = (step && !nccl && c->step_fusable) ? step : nullptr;
   int rc;
-  // fork: the one-body rows do not depend on K1 and run on the aux stream next to it
-  CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
-  CU_TRY(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
-  {
-    OneBodyParams ob;
-    ob.h = c->h;
-    ob.U = U;
-    ob.D = c->D;
-    ob.B1 = c->B1;
-    ob.B12 = c->B12;
-    ob.done_flag = done_flag;
-    ob.M = c->M;
-    ob.N = c->N;
-    ob.t0 = c->t0;
-    k_onebody<<<c->mloc, 256, 0, c->aux>>>(ob);
+  if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
+  if (c->generic) {
+    // no V4 symmetry: one term per index slot.  Slots 0,1 (rows t, q) come from
+    // the pass over g, slots 2,3 (rows r, s) from the pass over the pair-transposed tensor.
+    if ((rc = launch_prep(c, U, done_flag, 2, 3))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = launch_k1(c, U, done_flag, false, true))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = launch_tail(c, U, out, done_flag, false, 0, nullptr))) return rc;
+    if ((rc = launch_prep(c, U, done_flag, 4, 5))) return rc;
+    if ((rc = launch_k1(c, U, done_flag, true, true))) return rc;
+    if ((rc = launch_tail(c, U, out, done_flag, fused, 1, step_in_tail))) return rc;
+  } else {
+    if ((rc = launch_prep(c, U, done_flag, 0, pair ? 1 : -1))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = launch_k1(c, U, done_flag, false, true))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (!pair && c->mloc < c->M) {
+      // dense mode writes only the shard's rows; an in-place all-reduce of the previous
+      // evaluation may have left full rows elsewhere, so clear them
+      const size_t N = (size_t)c->N;
+      if (c->t0 > 0) CU_TRY(cudaMemsetAsync(out, 0, (size_t)c->t0 * N * sizeof(double), c->stream));
+      const size_t end = (size_t)(c->t0 + c->mloc);
+      if (end < (size_t)c->M)
+        CU_TRY(cudaMemsetAsync(out + end * N, 0, ((size_t)c->M - end) * N * sizeof(double),
+                               c->stream));
+    }
+    if ((rc = launch_tail(c, U, out, done_flag, fused, 0, step_in_tail))) return rc;
+  }
+  if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
+  if (nccl && (rc = do_allreduce(c, out, (size_t)c->M * c->N + 1))) return rc;
+  if (step && !step_in_tail) {
+    k_step<<<1, K3_THREADS, 0, c->stream>>>(*step);
     CU_TRY(cudaGetLastError());
     c->launches++;
   }
-  CU_TRY(cudaEventRecord(c->ev_join, c->aux));
-  if (c->generic) {
-    // no V4 symmetry: one slot term per index position.  Slots 0,1 come from
-    // the half transform of g, slots 2,3 from the half transform of the pair-transposed tensor.
-    if (c->world > 1 || c->mloc != c->M)
-      return fail(OO_ERR_UNSUPPORTED, "the generic (non-symmetric) path is single-GPU only");
-    if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if ((rc = launch_k1(c, U, done_flag, false))) return rc;
-    if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
-    if ((rc = launch_qc(c, done_flag, false))) return rc;
-    if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
-    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    if ((rc = launch_tail(c, U, out, done_flag, false, 0))) return rc;
-    if ((rc = launch_qc(c, done_flag, true))) return rc;
-    if ((rc = launch_tail(c, U, out, done_flag, false, 1))) return rc;
-    if ((rc = launch_k1(c, U, done_flag, true))) return rc;
-    if ((rc = launch_qc(c, done_flag, false))) return rc;
-    if ((rc = launch_tail(c, U, out, done_flag, false, 2))) return rc;
-    if ((rc = launch_qc(c, done_flag, true))) return rc;
-    if ((rc = launch_tail(c, U, out, done_flag, false, 3))) return rc;
-    if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
-    return OO_OK;
-  }
-  if (tm) CU_TRY(cudaEventRecord(c->ev[0], c->stream));
-  if ((rc = launch_k1(c, U, done_flag))) return rc;
-  if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
-  if ((rc = launch_qc(c, done_flag))) return rc;
-  if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
-  CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));   // join
-  if ((!c->pair_sym || c->generic) && c->mloc < c->M) {
-    // dense mode writes only the shard's rows; an in-place all-reduce of the previous evaluation
-    // may have left full rows elsewhere, so clear them
-    const size_t N = (size_t)c->N;
-    if (c->t0 > 0) CU_TRY(cudaMemsetAsync(out, 0, (size_t)c->t0 * N * sizeof(double), c->stream));
-    const size_t end = (size_t)(c->t0 + c->mloc);
-    if (end < (size_t)c->M)
-      CU_TRY(cudaMemsetAsync(out + end * N, 0, ((size_t)c->M - end) * N * sizeof(double),
-                             c->stream));
-  }
-  const bool fused = reduce && c->peer_on && c->world > 1;
-  if ((rc = launch_tail(c, U, out, done_flag, fused))) return rc;
-  if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
-  if (reduce && !fused && c->world > 1)
-    return do_allreduce(c, out, (size_t)c->M * c->N + 1);
   return OO_OK;
 }
 
@@ -432,6 +475,81 @@ int do_allreduce(oo_ctx* c, double* buf, size_t count) {
   if (!c->comm) return OO_OK;
   int r = g_nccl.all_reduce(buf, buf, count, kNcclFloat64, kNcclSum, c->comm, c->stream);
   if (r != 0) return fail(OO_ERR_NCCL, "ncclAllReduce: %s", g_nccl.get_error_string(r));
+  return OO_OK;
+}
+
+int alloc_zero(double** p, size_t n) {
+  if (*p) return OO_OK;
+  CU_TRY(cudaMalloc((void**)p, n * sizeof(double)));
+  CU_TRY(cudaMemset(*p, 0, n * sizeof(double)));
+  return OO_OK;
+}
+
+// Workspaces of the evaluation: 2-RDM layouts (kinds 0,1; 2..5 for the generic path), Q tensors,
+// per-slab records.
+int ensure_eval_ws(oo_ctx* c, bool generic) {
+  const size_t Np = c->Np, Np3 = Np * Np * Np;
+  int rc;
+  for (int k = generic ? 2 : 0; k < (generic ? 6 : 2); ++k)
+    if ((rc = alloc_zero(&c->G2[k], Np3 * Np))) return rc;
+  if ((rc = alloc_zero(&c->QA, (size_t)c->M * Np3))) return rc;
+  if ((rc = alloc_zero(&c->QB, (size_t)c->mloc * Np3))) return rc;
+  if ((rc = alloc_zero(&c->Aslab, (size_t)c->mloc * c->M * 2 * Np))) return rc;
+  return OO_OK;
+}
+
+// Workspaces of oo_transform (tile mode of K1, q-contraction).
+int ensure_transform_ws(oo_ctx* c) {
+  const size_t Np2 = (size_t)c->Np * c->Np;
+  int rc;
+  if ((rc = alloc_zero(&c->Y, (size_t)c->mloc * c->M * Np2))) return rc;
+  if ((rc = alloc_zero(&c->YT, (size_t)c->mloc * (c->M / 2 + 1) * Np2))) return rc;
+  if ((rc = alloc_zero(&c->Upad, (size_t)c->M * c->Np))) return rc;
+  if ((rc = alloc_zero(&c->T3, (size_t)c->M * c->Np * Np2))) return rc;
+  return OO_OK;
+}
+
+// 2-RDM in the layouts the evaluation needs (G_dev: [N]^4 spatial, spin-summed, weighted).
+int prepare_gammas(oo_ctx* c, const double* G_dev) {
+  int rc = ensure_eval_ws(c, c->generic);
+  if (rc) return rc;
+  for (int k = c->generic ? 2 : 0; k < (c->generic ? 6 : 2); ++k) {
+    k_prepare_gamma2<<<c->Np * c->Np, 256, 0, c->stream>>>(G_dev, c->G2[k], c->N, c->Np, k);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
+  return OO_OK;
+}
+
+// The fused all-reduce gave up waiting for a peer (slow callback, hung rank): every result since
+// then is NaN-poisoned on the device; report it from every synchronous entry point.
+int check_peer(oo_ctx* c) {
+  if (c->peer_on && c->peer_err_host && *c->peer_err_host)
+    return fail(OO_ERR_NCCL,
+                "fused all-reduce timed out after %.1f s waiting for a peer GPU; results since then "
+                "are invalid (NaN).  A host callback or a stalled rank can cause this: raise "
+                "OO_PEER_TIMEOUT_MS / oo_set_peer_timeout_ms or use the NCCL all-reduce",
+                c->peer_timeout_ns * 1e-9);
+  return OO_OK;
+}
+
+// Lazily created resources of the pipelined host-buffer evaluation (two slots).
+int ensure_slots(oo_ctx* c) {
+  if (c->slot_u[0]) return OO_OK;
+  const size_t MN = (size_t)c->M * c->N;
+  for (int s = 0; s < 2; ++s) {
+    CU_TRY(cudaMallocHost((void**)&c->slot_pin_u[s], MN * sizeof(double)));
+    CU_TRY(cudaMallocHost((void**)&c->slot_pin_out[s], (MN + 1) * sizeof(double)));
+    CU_TRY(cudaMalloc((void**)&c->slot_u[s], MN * sizeof(double)));
+    CU_TRY(cudaMalloc((void**)&c->slot_out[s], (MN + 1) * sizeof(double)));
+    CU_TRY(cudaMemset(c->slot_out[s], 0, (MN + 1) * sizeof(double)));
+    CU_TRY(cudaEventCreateWithFlags(&c->slot_h2d[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->slot_eval[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->slot_done[s], cudaEventDisableTiming));
+  }
+  CU_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaDeviceSynchronize());
   return OO_OK;
 }
 
@@ -517,18 +635,13 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     if (e == cudaSuccess) e = alloc(p, n);
     if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(double));
   };
-  A(&c->Y, (size_t)mloc * M * Np2);
-  A(&c->YT, (size_t)mloc * (M / 2 + 1) * Np2);
-  A(&c->Upad, (size_t)M * c->Np);
+  // the problem-sized workspaces (Q tensors, Aslab; Y / YT / T3 of oo_transform) are allocated by
+  // the first call that needs them: a context that only serves oo_orth / oo_bb_update stays small
+  (void)Np2;
   A(&c->Gtmp, (size_t)N * N * N * N);
   A(&c->B1, (size_t)mloc * N);
   A(&c->B12, (size_t)mloc * N);
-  A(&c->T3, (size_t)M * c->Np * Np2);
-  A(&c->Gp, (size_t)c->Np * c->Np * Np2);
   A(&c->D, (size_t)N * N);
-  A(&c->A, (size_t)M * N);
-  A(&c->UD, MN);
-  A(&c->UDt, MN);
   A(&c->rowE, (size_t)4 * M);
   A(&c->out, MN + 1);
   A(&c->Ucur, MN);
@@ -565,9 +678,10 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   // framework (torch) produces the input tensors unless told otherwise.
   if (e == cudaSuccess) e = cudaStreamCreate(&c->stream);
   c->own_stream = (e == cudaSuccess && c->stream != nullptr);   // so that a failed create frees it
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  {
+    const char* nf = getenv("OO_NO_STEP_FUSION");
+    c->step_fusable = !(nf && *nf && *nf != '0');
+  }
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
     e = cudaEventCreateWithFlags(&c->poll_ev[i], cudaEventDisableTiming);
@@ -589,16 +703,30 @@ int oo_destroy(oo_ctx* c) {
     cudaGraphExecDestroy(c->chunk_graph);
     c->chunk_graph = nullptr;
   }
-  if (c->aux) cudaStreamSynchronize(c->aux);
   if (c->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->comm);
   for (int r = 0; r < PEER_MAX; ++r)
     if (c->peer_map[r] && c->peer_map[r] != c->peer_base) cudaIpcCloseMemHandle(c->peer_map[r]);
-  for (int s2 = 0; s2 < 4; ++s2)
-    if (c->Gp_slot[s2]) cudaFree(c->Gp_slot[s2]);
+  for (int s2 = 0; s2 < 6; ++s2)
+    if (c->G2[s2]) cudaFree(c->G2[s2]);
+  if (c->QA) cudaFree(c->QA);
+  if (c->QB) cudaFree(c->QB);
+  if (c->Aslab) cudaFree(c->Aslab);
   if (c->peer_base) cudaFree(c->peer_base);
   if (c->peer_err) cudaFree(c->peer_err);
+  if (c->peer_err_host) cudaFreeHost((void*)c->peer_err_host);
+  for (int s2 = 0; s2 < 2; ++s2) {
+    if (c->slot_pin_u[s2]) cudaFreeHost(c->slot_pin_u[s2]);
+    if (c->slot_pin_out[s2]) cudaFreeHost(c->slot_pin_out[s2]);
+    if (c->slot_u[s2]) cudaFree(c->slot_u[s2]);
+    if (c->slot_out[s2]) cudaFree(c->slot_out[s2]);
+    if (c->slot_h2d[s2]) cudaEventDestroy(c->slot_h2d[s2]);
+    if (c->slot_eval[s2]) cudaEventDestroy(c->slot_eval[s2]);
+    if (c->slot_done[s2]) cudaEventDestroy(c->slot_done[s2]);
+  }
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->peer_seq_dev) cudaFree(c->peer_seq_dev);
-  double* bufs[] = {c->Y,   c->T3,   c->Gp,    c->D,     c->A,    c->UD,     c->UDt,      c->rowE,
+  double* bufs[] = {c->Y,   c->T3,   c->D,     c->rowE,
                     c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
                     c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};
   for (double* b : bufs)
@@ -614,12 +742,6 @@ int oo_destroy(oo_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->poll_ev)
     if (ev) cudaEventDestroy(ev);
-  if (c->aux) {
-    cudaStreamSynchronize(c->aux);
-    cudaStreamDestroy(c->aux);
-  }
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return OO_OK;
@@ -645,7 +767,7 @@ int oo_set_stream(oo_ctx* c, void* cuda_stream) {
 int oo_synchronize(oo_ctx* c) {
   if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
   CU_TRY(cudaStreamSynchronize(c->stream));
-  return OO_OK;
+  return check_peer(c);
 }
 
 int oo_set_integrals(oo_ctx* c, const double* h_dev, const double* g_dev, unsigned flags) {
@@ -659,6 +781,8 @@ int oo_set_integrals(oo_ctx* c, const double* h_dev, const double* g_dev, unsign
   const bool packed = (flags & OO_G_PAIR_PACKED) != 0;
   int rc = build_tmap(c, g_dev, &c->tmap, packed ? (size_t)c->nsel : 0);
   if (rc) return rc;
+  if ((rc = ensure_eval_ws(c, false))) return rc;
+  if (c->generic) c->have_rdms = false;   // the 2-RDM layouts of the symmetric path are not prepared
   c->h = h_dev;
   c->g = g_dev;
   c->gflags = flags;
@@ -705,7 +829,6 @@ int oo_set_integrals_generic(oo_ctx* c, const double* h_dev, const double* g_dev
   if (!c || !h_dev || !g_dev || !g_pair_transposed_dev) return fail(OO_ERR_INVALID, "NULL argument");
   if ((((uintptr_t)g_dev) | ((uintptr_t)g_pair_transposed_dev)) & 15)
     return fail(OO_ERR_INVALID, "g must be 16-byte aligned");
-  if (c->mloc != c->M) return fail(OO_ERR_UNSUPPORTED, "the generic path is single-GPU only");
   CU_TRY(cudaSetDevice(c->device));
   c->h = h_dev;
   c->g = g_dev;
@@ -715,16 +838,10 @@ int oo_set_integrals_generic(oo_ctx* c, const double* h_dev, const double* g_dev
   int rc = build_tmap(c, c->g, &c->tmap);
   if (rc) return rc;
   if ((rc = build_tmap(c, c->g2, &c->tmap2))) return rc;
-  if (!c->Gp_slot[0]) {
-    const size_t n = (size_t)c->Np * c->Np * c->Np * c->Np;
-    for (int s = 0; s < 4; ++s) {
-      CU_TRY(cudaMalloc((void**)&c->Gp_slot[s], n * sizeof(double)));
-      CU_TRY(cudaMemset(c->Gp_slot[s], 0, n * sizeof(double)));
-    }
-  }
+  if ((rc = ensure_eval_ws(c, true))) return rc;
+  if (!c->generic) c->have_rdms = false;   // the 2-RDM must be re-ingested in the four slot layouts
   c->generic = true;
   c->have_ints = true;
-  c->have_rdms = false;   // the 2-RDM must be re-ingested in the four slot layouts
   return OO_OK;
 }
 
@@ -754,22 +871,17 @@ int oo_set_rdms(oo_ctx* c, const double* D_dev, const double* G_dev) {
   CU_TRY(cudaSetDevice(c->device));
   CU_TRY(cudaMemcpyAsync(c->D, D_dev, (size_t)c->N * c->N * sizeof(double),
                          cudaMemcpyDeviceToDevice, c->stream));
-  k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp, c->N, c->Np, 1);
-  CU_TRY(cudaGetLastError());
-  c->launches++;
-  if (c->generic)
-    for (int s = 0; s < 4; ++s) {
-      k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp_slot[s], c->N, c->Np, 0, s);
-      CU_TRY(cudaGetLastError());
-      c->launches++;
-    }
+  int rc = prepare_gammas(c, G_dev);
+  if (rc) return rc;
   c->have_rdms = true;
   return OO_OK;
 }
 
-int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
-                     double* g_sp_out_dev, unsigned* block_mask, double* stats_host) {
-  if (!g_spin_dev || !g_sp_out_dev || !block_mask || M < 1)
+int oo_ingest_spin_g_rows(int device, const double* g_spin_dev, int M, double rtol, int t0,
+                          int mloc, int Mpad, double* g_out_dev, unsigned* block_mask,
+                          double* stats_host) {
+  if (!g_spin_dev || !g_out_dev || !block_mask || M < 1 || t0 < 0 || mloc < 1 || t0 + mloc > M ||
+      Mpad < M)
     return fail(OO_ERR_INVALID, "bad argument");
   CU_TRY(cudaSetDevice(device));
   unsigned long long* d = nullptr;
@@ -794,7 +906,7 @@ int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
       if (ref < 0) ref = b;
     }
   if (ref < 0) ref = 0;  // all-zero tensor: take the alpha-alpha-alpha-alpha block
-  k_spin_block_extract<<<148 * 4, 256>>>(g_spin_dev, M, ref, mask, g_sp_out_dev, d + 16);
+  k_spin_block_extract<<<148 * 4, 256>>>(g_spin_dev, M, ref, mask, t0, mloc, Mpad, g_out_dev, d + 16);
   e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpy(bits, d + 16, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -813,6 +925,12 @@ int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
                 "unrestricted two-body integrals: non-zero spin blocks differ (max deviation %.3e, "
                 "max |g| %.3e)", dev_max, gmax);
   return OO_OK;
+}
+
+int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
+                     double* g_sp_out_dev, unsigned* block_mask, double* stats_host) {
+  return oo_ingest_spin_g_rows(device, g_spin_dev, M, rtol, 0, M, M, g_sp_out_dev, block_mask,
+                               stats_host);
 }
 
 int oo_set_rdms_spin(oo_ctx* c, const double* const* D_spin_dev, const double* const* G_spin_dev,
@@ -836,16 +954,9 @@ int oo_set_rdms_spin(oo_ctx* c, const double* const* D_spin_dev, const double* c
   const int grid = (int)std::min<size_t>((N4 + 255) / 256, 148 * 8);
   k_rdm_spin_sum<<<grid, 256, 0, c->stream>>>(rp, c->D, c->Gtmp);
   CU_TRY(cudaGetLastError());
-  k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(c->Gtmp, c->Gp, c->N, c->Np, 1);
-  CU_TRY(cudaGetLastError());
-  if (c->generic)
-    for (int s = 0; s < 4; ++s) {
-      k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(c->Gtmp, c->Gp_slot[s], c->N, c->Np, 0,
-                                                         s);
-      CU_TRY(cudaGetLastError());
-      c->launches++;
-    }
-  c->launches += 2;
+  c->launches++;
+  int rc = prepare_gammas(c, c->Gtmp);
+  if (rc) return rc;
   c->have_rdms = true;
   return OO_OK;
 }
@@ -862,20 +973,48 @@ int oo_energy_grad_allreduce(oo_ctx* c, const double* U_dev, double* out_dev) {
   return enqueue_eval(c, U_dev, out_dev ? out_dev : c->out, nullptr, true);
 }
 
+int oo_eval_submit(oo_ctx* c, const double* U_host, int slot) {
+  if (!c || !U_host || slot < 0 || slot > 1) return fail(OO_ERR_INVALID, "bad argument");
+  if (!c->have_ints || !c->have_rdms) return fail(OO_ERR_STATE, "integrals / RDMs not set");
+  CU_TRY(cudaSetDevice(c->device));
+  int rc = ensure_slots(c);
+  if (rc) return rc;
+  if (c->slot_busy[slot]) return fail(OO_ERR_STATE, "slot %d still holds an unread result", slot);
+  const size_t MN = (size_t)c->M * c->N;
+  memcpy(c->slot_pin_u[slot], U_host, MN * sizeof(double));
+  // H2D on its own stream (overlaps the evaluation that is running), evaluation on the context
+  // stream, D2H on a third stream (overlaps the next evaluation)
+  CU_TRY(cudaMemcpyAsync(c->slot_u[slot], c->slot_pin_u[slot], MN * sizeof(double),
+                         cudaMemcpyHostToDevice, c->h2d_stream));
+  CU_TRY(cudaEventRecord(c->slot_h2d[slot], c->h2d_stream));
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->slot_h2d[slot], 0));
+  if ((rc = enqueue_eval(c, c->slot_u[slot], c->slot_out[slot], nullptr, true))) return rc;
+  CU_TRY(cudaEventRecord(c->slot_eval[slot], c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->d2h_stream, c->slot_eval[slot], 0));
+  CU_TRY(cudaMemcpyAsync(c->slot_pin_out[slot], c->slot_out[slot], (MN + 1) * sizeof(double),
+                         cudaMemcpyDeviceToHost, c->d2h_stream));
+  CU_TRY(cudaEventRecord(c->slot_done[slot], c->d2h_stream));
+  c->slot_busy[slot] = true;
+  return OO_OK;
+}
+
+int oo_eval_wait(oo_ctx* c, int slot, double* E_host, double* grad_host) {
+  if (!c || slot < 0 || slot > 1) return fail(OO_ERR_INVALID, "bad argument");
+  if (!c->slot_busy[slot]) return fail(OO_ERR_STATE, "nothing was submitted to slot %d", slot);
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaEventSynchronize(c->slot_done[slot]));
+  c->slot_busy[slot] = false;
+  const size_t MN = (size_t)c->M * c->N;
+  if (E_host) *E_host = c->slot_pin_out[slot][MN];
+  if (grad_host) memcpy(grad_host, c->slot_pin_out[slot], MN * sizeof(double));
+  return check_peer(c);
+}
+
 int oo_energy_grad_host(oo_ctx* c, const double* U_host, double* E_host, double* grad_host) {
   if (!c || !U_host || !E_host) return fail(OO_ERR_INVALID, "NULL argument");
-  CU_TRY(cudaSetDevice(c->device));
-  const size_t MN = (size_t)c->M * c->N;
-  memcpy(c->pin, U_host, MN * sizeof(double));
-  CU_TRY(cudaMemcpyAsync(c->Ucur, c->pin, MN * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  int rc = enqueue_eval(c, c->Ucur, c->out, nullptr, true);
+  int rc = oo_eval_submit(c, U_host, 0);
   if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(c->pin, c->out, (MN + 1) * sizeof(double), cudaMemcpyDeviceToHost,
-                         c->stream));
-  CU_TRY(cudaStreamSynchronize(c->stream));
-  *E_host = c->pin[MN];
-  if (grad_host) memcpy(grad_host, c->pin, MN * sizeof(double));
-  return OO_OK;
+  return oo_eval_wait(c, 0, E_host, grad_host);
 }
 
 int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_rot_dev) {
@@ -884,7 +1023,8 @@ int oo_transform(oo_ctx* c, const double* U_dev, double* h_rot_dev, double* g_ro
   CU_TRY(cudaSetDevice(c->device));
   int rc;
   if (g_rot_dev) {
-    if ((rc = launch_k1(c, U_dev, nullptr))) return rc;
+    if ((rc = ensure_transform_ws(c))) return rc;
+    if ((rc = launch_k1(c, U_dev, nullptr, false, false))) return rc;
     if ((rc = launch_qc(c, nullptr))) return rc;
     k_rotate_g<<<c->N * c->N, 256, 0, c->stream>>>(c->T3, U_dev, g_rot_dev, c->N, c->Np,
                                                    (c->pair_sym && !c->generic) ? 0 : c->t0,
@@ -984,28 +1124,25 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   // no-ops (every kernel tests the flag first).
   const int chunk = 4;
   const long max_transitions = (long)std::max(maxiter, 3) + 4;
+  c->stop_requested = 0;
   long enq = 0;
   int slot = 0;
   bool pending[2] = {false, false};
   bool done = false;
   auto chunk_body = [&]() -> int {
     int rc;
-    for (int i = 0; i < chunk; ++i) {
-      if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag, true))) return rc;
-      k_step<<<1, K3_THREADS, 0, c->stream>>>(sp);
-      CU_TRY(cudaGetLastError());
-      c->launches++;
-    }
+    for (int i = 0; i < chunk; ++i)
+      if ((rc = enqueue_eval(c, c->Ucur, c->out, done_flag, true, &sp))) return rc;
     return OO_OK;
   };
-  // The chunk (4 x [one-body | K1, q-contraction, tail(+all-reduce), step]) is captured once into
+  // The chunk (4 x [k_prepare_q, K1, k_tail_reduce(+all-reduce, +step)]) is captured once into
   // a CUDA graph and replayed: the inner loop of small problems is launch-bound.  The first chunk
   // runs un-captured (it also performs the one-time function-attribute calls).
   const bool use_graph = !c->timing && getenv("OO_NO_GRAPH") == nullptr;
   const void* key[10] = {c->E_hist, (const void*)(uintptr_t)c->hist_cap, c->stream, c->g, c->g2,
                          c->h, c->comm, (const void*)(uintptr_t)(c->pair_sym + 2 * c->generic +
                                                                  4 * c->peer_on + 8 * c->packed),
-                         c->Gp_slot[0], (const void*)(uintptr_t)c->world};
+                         c->QA, (const void*)(uintptr_t)(c->world + 16 * c->step_fusable)};
   bool first_chunk = true;
   long chunk_start[2] = {0, 0};
   double prev_f = 0.0;          // f(U_{k-1}) carried across chunks for the callback replay
@@ -1078,9 +1215,21 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
     CU_TRY(cudaEventSynchronize(c->poll_ev[slot]));
     pending[slot] = false;
     deliver_callbacks(slot);
+    if (c->stop_requested == 1) {
+      // a callback asked for an early stop: raise the device-side flag behind the queued work
+      k_force_stop<<<1, 1, 0, c->stream>>>(c->state);
+      CU_TRY(cudaGetLastError());
+      c->stop_requested = 2;
+    }
     if (c->pin_state[slot].done) {
       done = true;
     } else if (!pending[other]) {
+      if (c->stop_requested) {                 // the forced stop is queued behind the last chunk
+        CU_TRY(cudaMemcpyAsync(&c->pin_state[other], c->state, sizeof(OptState),
+                               cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (c->pin_state[other].done) break;
+      }
       return fail(OO_ERR_NUMERIC, "optimiser did not stop within %ld transitions", enq);
     }
     slot = other;
@@ -1100,7 +1249,23 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   if (bb_final) *bb_final = fin.alpha;
   c->last_ns_iters = fin.ns_iters;
   c->last_jacobi_calls = fin.jacobi_calls;
+  {
+    int prc = check_peer(c);
+    if (prc) return prc;
+  }
   if (fin.nan_flag) return fail(OO_ERR_NUMERIC, "non-finite value met during the optimisation");
+  return OO_OK;
+}
+
+int oo_request_stop(oo_ctx* c) {
+  if (!c) return fail(OO_ERR_INVALID, "ctx is NULL");
+  c->stop_requested = 1;
+  return OO_OK;
+}
+
+int oo_set_peer_timeout_ms(oo_ctx* c, double milliseconds) {
+  if (!c || !(milliseconds > 0)) return fail(OO_ERR_INVALID, "bad argument");
+  c->peer_timeout_ns = (unsigned long long)(milliseconds * 1e6);
   return OO_OK;
 }
 
@@ -1149,6 +1314,13 @@ int oo_peer_export(oo_ctx* c, void* handle64_host) {
     CU_TRY(cudaMemset(c->peer_base, 0, bytes));
     CU_TRY(cudaMalloc((void**)&c->peer_err, sizeof(int)));
     CU_TRY(cudaMemset(c->peer_err, 0, sizeof(int)));
+    CU_TRY(cudaHostAlloc((void**)&c->peer_err_host, sizeof(int), cudaHostAllocMapped));
+    *c->peer_err_host = 0;
+    CU_TRY(cudaHostGetDevicePointer((void**)&c->peer_err_host_dev, (void*)c->peer_err_host, 0));
+    if (const char* t = getenv("OO_PEER_TIMEOUT_MS")) {
+      const double ms = atof(t);
+      if (ms > 0) c->peer_timeout_ns = (unsigned long long)(ms * 1e6);
+    }
     CU_TRY(cudaMalloc((void**)&c->peer_seq_dev, sizeof(unsigned long long)));
     CU_TRY(cudaMemset(c->peer_seq_dev, 0, sizeof(unsigned long long)));
     CU_TRY(cudaDeviceSynchronize());
@@ -1188,7 +1360,7 @@ int oo_peer_status(oo_ctx* c) {
   if (!c->peer_on) return 0;
   int err = 0;
   CU_TRY(cudaMemcpy(&err, c->peer_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) return fail(OO_ERR_NCCL, "fused all-reduce timed out waiting for a peer");
+  if (err || check_peer(c)) return fail(OO_ERR_NCCL, "fused all-reduce timed out waiting for a peer");
   return 1;
 }
 
@@ -1227,7 +1399,9 @@ int oo_last_timing(oo_ctx* c, float* ms5_host) {
   if (!c || !ms5_host) return fail(OO_ERR_INVALID, "NULL argument");
   if (!c->timing) return fail(OO_ERR_STATE, "timing is not enabled");
   CU_TRY(cudaEventSynchronize(c->ev[3]));
-  for (int i = 0; i < 3; ++i) CU_TRY(cudaEventElapsedTime(&ms5_host[i], c->ev[i], c->ev[i + 1]));
+  CU_TRY(cudaEventElapsedTime(&ms5_host[0], c->ev[1], c->ev[2]));   // K1
+  CU_TRY(cudaEventElapsedTime(&ms5_host[1], c->ev[0], c->ev[1]));   // k_prepare_q
+  CU_TRY(cudaEventElapsedTime(&ms5_host[2], c->ev[2], c->ev[3]));   // k_tail_reduce
   ms5_host[3] = 0.f;
   CU_TRY(cudaEventElapsedTime(&ms5_host[4], c->ev[0], c->ev[3]));
   return OO_OK;

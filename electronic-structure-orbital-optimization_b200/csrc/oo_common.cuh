@@ -94,8 +94,23 @@ __device__ __forceinline__ void st_global_hint(double* addr, double v, uint64_t 
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(policy)
                : "memory");
 }
+// 16-byte read-only load with an L2 eviction-priority hint.
+__device__ __forceinline__ double2 ldg128_hint(const double* addr, uint64_t policy) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(addr), "l"(policy));
+  return v;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// Nanosecond wall clock of the device (independent of the SM clock).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // Named barrier for a subset of the CTA (id 1..15; id 0 is __syncthreads).

@@ -65,36 +65,43 @@ __global__ void __launch_bounds__(256) k_v4_symmetry_tiles(const double* __restr
   }
 }
 
-// Logical Gp[a][j][l*Np+k] = (1/4)(G[a,j,k,l] + G[j,a,l,k] + G[k,l,a,j] + G[l,k,j,a])  (V4 average),
-// zero in the padding (j, k or l >= N).  grid N*Np, block Np*Np threads (looped).
-// symmetrise = 0 selects one of the four slot layouts of the generic (no symmetry) gradient:
-//   slot 0: Gp[a][j][l*Np+k] = G[a,j,k,l]      slot 1: Gp[a][i][l*Np+k] = G[i,a,k,l]
-//   slot 2: Gp[a][l][j*Np+i] = G[i,j,a,l]      slot 3: Gp[a][k][j*Np+i] = G[i,j,k,a]
-// (middle index = the plane index of T3, tile index = (row, col) of the K1 tile as stored).
-__global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict__ Gp, int N, int Np,
-                                int symmetrise, int slot = 0) {
-  const int a = blockIdx.x / Np, j = blockIdx.x % Np;
+// 2-RDM in the layout of the fused evaluation (k_prepare_q): G2[c][a][e], c = the index that is
+// contracted with U, a = the gradient column, e = e1*Np + e0 the position inside a K1 tile
+// (tile[e1*Np + e0] = Y[e0][e1], Y = U^T g_slab U).  Zero in the padding.  `kind` selects what is
+// summed over which orbital (see oo_k1.cuh / DESIGN.md section 1):
+//   0  V4 own     G2[j][a][l*Np+k] = Gs[a,j,k,l]   Gs = V4 average of G   (row t from slab (t,q), c = q side)
+//   1  V4 mirror  G2[j][a][k*Np+l] = Gs[a,j,k,l]   (row q from slab (t,q): transposed tile, c = t side)
+//   2  slot 0     G2[j][a][l*Np+k] = G[a,j,k,l]    generic pass over g:    row t, c = q
+//   3  slot 1     G2[i][a][l*Np+k] = G[i,a,k,l]    generic pass over g:    row q, c = t
+//   4  slot 2     G2[l][a][j*Np+i] = G[i,j,a,l]    generic pass over g_pt: row r, c = s
+//   5  slot 3     G2[k][a][j*Np+i] = G[i,j,k,a]    generic pass over g_pt: row s, c = r
+// grid Np*Np (c, a), block 256 over e.
+__global__ void k_prepare_gamma2(const double* __restrict__ G, double* __restrict__ G2, int N,
+                                 int Np, int kind) {
+  const int c = blockIdx.x / Np, a = blockIdx.x % Np;
   const int Np2 = Np * Np;
   const size_t N2 = (size_t)N * N, N3 = N2 * N;
+  auto at = [&](int i0, int i1, int i2, int i3) {
+    return G[i0 * N3 + i1 * N2 + (size_t)i2 * N + i3];
+  };
   for (int e = threadIdx.x; e < Np2; e += blockDim.x) {
-    const int l = e / Np, k = e - l * Np;
+    const int e1 = e / Np, e0 = e - e1 * Np;
     double v = 0.0;
-    if (j < N && k < N && l < N) {
-      if (!symmetrise && slot == 1) v = G[j * N3 + a * N2 + (size_t)k * N + l];
-      else if (!symmetrise && slot == 2) v = G[k * N3 + l * N2 + (size_t)a * N + j];
-      else if (!symmetrise && slot == 3) v = G[k * N3 + l * N2 + (size_t)j * N + a];
-      else v = G[a * N3 + j * N2 + (size_t)k * N + l];
-      if (symmetrise) {
-        v += G[j * N3 + a * N2 + (size_t)l * N + k];
-        v += G[k * N3 + l * N2 + (size_t)a * N + j];
-        v += G[l * N3 + k * N2 + (size_t)j * N + a];
-        v *= 0.25;
+    if (c < N && a < N && e0 < N && e1 < N) {
+      if (kind <= 1) {
+        const int k = kind == 0 ? e0 : e1, l = kind == 0 ? e1 : e0, j = c;
+        v = 0.25 * (at(a, j, k, l) + at(j, a, l, k) + at(k, l, a, j) + at(l, k, j, a));
+      } else if (kind == 2) {
+        v = at(a, c, e0, e1);
+      } else if (kind == 3) {
+        v = at(c, a, e0, e1);
+      } else if (kind == 4) {
+        v = at(e0, e1, a, c);
+      } else {
+        v = at(e0, e1, c, a);
       }
     }
-    // storage: a fastest, Gp[(j*Np2 + e)*Np + a] (rows a >= N stay zero from the allocation):
-    // the tail kernel reads all a of one (j,e) with unit stride; strides of Np^3 doubles between
-    // the a-planes made every CTA hit the same L2 slices at the same time (measured 10x slower)
-    Gp[((size_t)j * Np2 + e) * Np + a] = v;
+    G2[((size_t)c * Np + a) * Np2 + e] = v;
   }
 }
 
@@ -139,24 +146,29 @@ __global__ void k_spin_block_maxabs(const double* __restrict__ g, int M, unsigne
   if (threadIdx.x < 16 && s_max[threadIdx.x]) atomicMax(stats + threadIdx.x, s_max[threadIdx.x]);
 }
 
-// out[pqrs] = g[block ref](pqrs) and diff[b] = max |g[block b] - g[block ref]| for blocks in mask.
+// out[tl][q][r][s] = g[block ref](t0+tl, q, r, s) for tl < mloc, written with extent Mp >= M in
+// the last three indices (Mp = M+1 pads an odd M for TMA; the padding is left untouched, i.e.
+// zero from the caller's allocation), and diff[b] = max |g[block b] - g[block ref]| over the same
+// rows for the blocks in mask.
 __global__ void k_spin_block_extract(const double* __restrict__ g, int M, int ref, unsigned mask,
-                                     double* __restrict__ out, unsigned long long* diff) {
-  const size_t P = 2 * (size_t)M, M4 = (size_t)M * M * M * M;
+                                     int t0, int mloc, int Mp, double* __restrict__ out,
+                                     unsigned long long* diff) {
+  const size_t P = 2 * (size_t)M, total = (size_t)mloc * M * M * M;
   const size_t P3 = P * P * P, P2 = P * P;
   double dmax[16];
 #pragma unroll
   for (int b = 0; b < 16; ++b) dmax[b] = 0.0;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int s = (int)(idx % M), r = (int)((idx / M) % M), q = (int)((idx / ((size_t)M * M)) % M),
-              p = (int)(idx / ((size_t)M * M * M));
+              tl = (int)(idx / ((size_t)M * M * M));
+    const int p = t0 + tl;
     auto at = [&](int b) {
       return g[(size_t)(p + M * ((b >> 3) & 1)) * P3 + (size_t)(q + M * ((b >> 2) & 1)) * P2 +
                (size_t)(r + M * ((b >> 1) & 1)) * P + (size_t)(s + M * (b & 1))];
     };
     const double v = at(ref);
-    out[idx] = v;
+    out[(((size_t)tl * Mp + q) * Mp + r) * Mp + s] = v;
 #pragma unroll
     for (int b = 0; b < 16; ++b)
       if ((mask >> b) & 1u) dmax[b] = fmax(dmax[b], fabs(at(b) - v));

@@ -16,10 +16,20 @@
 //                                                 the 8x8 C fragment of m8n8k4 is two 8x4 A
 //                                                 fragments with a permuted k order), B = U^T (smem)
 // Work decomposition: persistent CTAs (one per SM), slabs dealt round-robin; inside a CTA one TMA
-// producer warp, one epilogue warp (per-slab reduction + stores, off the MMA critical path) and
+// producer warp, two epilogue warps (per-slab reduction, off the MMA critical path) and
 // 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
 // the current 256-row pass and all of its columns, so the second contraction costs a fixed N/M
 // fraction of the first.
+//
+// Fused 2-RDM contraction (energy / gradient evaluations).  The rows of A = dE2/dU / 4 are
+//      A[t][a] = sum_q <Y_tq, QA_q[a]>   +   sum_{t'} <Y_t't, QB_t'[a]>   (second sum: pair mode)
+// with QA_q[a][e] = sum_j U[q][j] Gamma~[a][j][e] (k_prepare_q; depends on U and the 2-RDM only).
+// The epilogue warps therefore never store the N x N tiles: warp A takes the dot products of the
+// finished tile with QA_q (row t of A), warp B with QB_t (row q of A: the transposed tile of the
+// pair partner, the transposition folded into QB's layout), and they write 2 x Np doubles per
+// slab (Aslab).  The tiles, the q-contraction and the T3 tensor disappear from the evaluation;
+// what is left after K1 is a fixed-order sum of Aslab records per row (k_tail_reduce).
+// Tile mode (p.QA == NULL; oo_transform only) stores Y (warp A) and its transpose (warp B).
 #pragma once
 #include "oo_common.cuh"
 
@@ -30,11 +40,11 @@ constexpr int K1_RB = 4;                           // 8-row blocks per consumer 
 constexpr int K1_ROWS = K1_NWARP * K1_RB * 8;      // slab rows per pass = TMA box height (256)
 constexpr int K1_KC = 16;                          // slab columns per stage (128 B swizzle span)
 constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
-constexpr int K1_THREADS = (K1_NWARP + 2) * 32;    // + 1 TMA producer warp + 1 epilogue warp
+constexpr int K1_THREADS = (K1_NWARP + 3) * 32;    // + 1 TMA producer warp + 2 epilogue warps
 constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
 constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
 constexpr int K1_BAR_FOLD = 3;                     // first of the two-warp hand-over barriers (ids 3..12)
-constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + epilogue warp
+constexpr int K1_BAR_COUNT = (K1_NWARP + 2) * 32;  // consumers + the two epilogue warps
 
 struct K1Params {
   const double* U;       // [M][N] row-major partial unitary
@@ -54,6 +64,11 @@ struct K1Params {
                          // them in L2 (used when Y + YT are a small part of L2)
   int npart;             // partial-tile buffers at slab end: 8 (one per warp), 4 or 2 (warps are
                          // folded into them in fixed order; frees smem for one more TMA stage)
+  // ---- fused 2-RDM contraction (QA != NULL) ----
+  const double* QA;      // [M][Np][Np*Np]    QA_q[a][e], rows of all partner orbitals q
+  const double* QB;      // [mloc][Np][Np*Np] QB_t[a][e], rows of this GPU's shard (NULL: no second dot)
+  double* Aslab;         // [nslab][2][Np]: <tile, QA_q[a]> and <tile, QB_t[a]> of every streamed slab
+  const int* slab_tq;    // slab i is (tl, q) with slab_tq[i] = tl*M + q; NULL = i (dense order)
 };
 
 // Dynamic shared memory needed by k1_half_transform<NT> (before 1024 B alignment slack).
@@ -181,7 +196,7 @@ __device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&ya
   k1_second_gemm_n<NT, NACT>(yacc, acc, ub2, s.u_nt_stride);
 }
 
-// 10 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
+// 11 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
 // 65536 / 384 = 168 per thread (ptxas -v: NT = 1: 89, NT = 2: 125, NT = 3: 168 without spills,
 // NT = 4: 168 with ~0.9 KB of spills -- it still reaches 29 TFLOP/s).
 template <int NT>
@@ -259,31 +274,91 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     return;
   }
 
-  if (warp == K1_NWARP + 1) {
-    // ------------------------------ epilogue warp ------------------------------
-    // Takes the per-slab reduction off the consumers' critical path: they only drop their
-    // partial tiles into shared memory and go on with the next slab; this warp sums the 8
-    // partials in fixed order (deterministic) and stores the tile and its transpose.
+  if (warp > K1_NWARP) {
+    // ------------------------------ epilogue warps ------------------------------
+    // Take the per-slab reduction off the consumers' critical path: they only drop their
+    // partial tiles into shared memory and go on with the next slab.  Both warps sum the
+    // partials in fixed order (deterministic) into registers and release the buffer at once.
+    const bool second = warp == K1_NWARP + 2;
+    constexpr int NCH = Np * Np / 64;                      // 16-byte chunks of the tile per lane
     named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);           // the buffer starts out free
+    if (p.QA != nullptr) {
+      // ---- fused mode: dot products with the Q tensors, 2 x Np doubles per slab ----
+      const uint64_t keep = l2_policy_evict_last();
+      const bool active = !second || p.QB != nullptr;
+      for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+        const int tq = p.slab_tq ? __ldg(p.slab_tq + slab) : slab;
+        named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
+        double2 tile[NCH];
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            double2 s2 = make_double2(0.0, 0.0);
+            for (int w = 0; w < p.npart; ++w) {
+              const double2 v =
+                  *reinterpret_cast<const double2*>(Ypart + w * Np * Np + 64 * i + 2 * lane);
+              s2.x += v.x;
+              s2.y += v.y;
+            }
+            tile[i] = s2;
+          }
+        }
+        named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
+        if (!active) continue;
+        const int tl = tq / p.M, q = tq - tl * p.M;
+        const double* Q = second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np;
+        double acc[Np];
+#pragma unroll
+        for (int a = 0; a < Np; ++a) acc[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+          for (int a0 = 0; a0 < Np; a0 += 8) {
+            double2 qv[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              qv[a] = ldg128_hint(Q + (size_t)(a0 + a) * Np * Np + 64 * i + 2 * lane, keep);
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              acc[a0 + a] = fma(tile[i].x, qv[a].x, fma(tile[i].y, qv[a].y, acc[a0 + a]));
+          }
+        }
+        double mine = 0.0;
+#pragma unroll
+        for (int a = 0; a < Np; ++a) {
+          double v = acc[a];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == a) mine = v;
+        }
+        if (lane < Np) p.Aslab[((size_t)slab * 2 + (second ? 1 : 0)) * Np + lane] = mine;
+      }
+      return;
+    }
+    // ---- tile mode: warp A stores the tile, warp B its transpose (pair-symmetric mode) ----
     const uint64_t keep = l2_policy_evict_last();
     for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
       named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
-      double* out = p.Y + (size_t)slab * Np * Np;
-      double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
-      for (int e = lane; e < Np * Np; e += 32) {
+      double* out = second ? (p.YT ? p.YT + (size_t)slab * Np * Np : nullptr)
+                           : p.Y + (size_t)slab * Np * Np;
+      double sums[Np * Np / 32];
+#pragma unroll
+      for (int i = 0; i < Np * Np / 32; ++i) {
         double s = 0.0;
-        for (int w = 0; w < p.npart; ++w) s += Ypart[w * Np * Np + e];
-        // transposed copy (2 KB per 512 KB slab) so that the pair-symmetric q-contraction
-        // reads both orientations with unit stride
-        if (p.l2_hints & 2) {
-          st_global_hint(out + e, s, keep);
-          if (outT) st_global_hint(outT + (e % Np) * Np + e / Np, s, keep);
-        } else {
-          out[e] = s;
-          if (outT) outT[(e % Np) * Np + e / Np] = s;
-        }
+        for (int w = 0; w < p.npart; ++w) s += Ypart[w * Np * Np + i * 32 + lane];
+        sums[i] = s;
       }
       named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
+      if (out == nullptr) continue;
+#pragma unroll
+      for (int i = 0; i < Np * Np / 32; ++i) {
+        const int e = i * 32 + lane;
+        // the transposed copy lets the pair-symmetric q-contraction read both orientations
+        // with unit stride
+        double* dst = second ? out + (e % Np) * Np + e / Np : out + e;
+        if (p.l2_hints & 2) st_global_hint(dst, sums[i], keep);
+        else *dst = sums[i];
+      }
     }
     return;
   }

@@ -1,8 +1,10 @@
-// K2 family — the cheap tail of the energy/gradient evaluation (HBM/L2-bound, no tensor cores):
-//   k_qcontract      T3[x][j][e]  = sum_q U[q][j] * Y[x,q][e]                (third index contraction)
-//   k_onebody        (h U D^T)[x], (h^T U D)[x] for the shard's rows   (1-RDM terms; aux stream)
-//   k_tail_row       A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]  (2-RDM contraction), dE/dU
-//                    rows, partial energy; fixed-order reductions, one launch
+// K2 family — everything of an evaluation around K1 (HBM/L2-bound, no tensor cores):
+//   k_prepare_q      Q tensors QA_q[a][e] = sum_j U[q][j] Gamma~[a][j][e] (+ QB for the mirrored
+//                    rows) and the one-body rows (h U D^T)[x], (h^T U D)[x] of the shard: what K1's
+//                    epilogue contracts the finished tiles with
+//   k_tail_reduce    fixed-order sum of K1's per-slab records into dE/dU rows, partial energy,
+//                    one-shot all-reduce over peer memory, optimiser transition (oo_optimize)
+//   k_qcontract      T3[x][j][e]  = sum_q U[q][j] * Y[x,q][e]      (oo_transform only)
 //   k_rotate_g       g'[i][j][k][l] = sum_x U[x][i] * T3[x][j][k][l]          (rotated Hamiltonian)
 // Together with K1 they restate, in the spatial-orbital picture and with an analytic gradient,
 //   base_opt_orb_solver.py:554-563 (energy) and
@@ -17,6 +19,7 @@
 // (M*N+1)-double all-reduce that exists anyway completes them.
 #pragma once
 #include "oo_common.cuh"
+#include "oo_k3.cuh"
 
 namespace oo {
 
@@ -190,59 +193,7 @@ __global__ void __launch_bounds__(QC_THREADS, NT <= 2 ? 2 : 1) k_qcontract(const
   }
 }
 
-// One-body gradient rows of this GPU's shard (independent of K1: runs on the aux stream).
-//   B1[xl][a]  = (h U D^T)[x][a]            B12[xl][a] = (h U D^T + h^T U D)[x][a],  x = t0 + xl
-// grid mloc, block 256.
-struct OneBodyParams {
-  const double* h;   // [M][M]
-  const double* U;   // [M][N]
-  const double* D;   // [N][N]
-  double* B1;        // [mloc][N]
-  double* B12;       // [mloc][N]
-  const int* done_flag;
-  int M, N, t0;
-};
-
-__global__ void __launch_bounds__(256) k_onebody(const OneBodyParams p) {
-  if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ double s_r1[256], s_r2[256], s_hu[32], s_htu[32];
-  const int tid = threadIdx.x, N = p.N, M = p.M;
-  const int x = p.t0 + blockIdx.x;
-  const int j = tid % N, part = tid / N, nparts = 256 / N;
-  double r1 = 0.0, r2 = 0.0;
-  if (part < nparts) {
-#pragma unroll 4
-    for (int q = part; q < M; q += nparts) {
-      const double u = __ldg(p.U + (size_t)q * N + j);
-      r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
-      r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
-    }
-  }
-  s_r1[tid] = r1;
-  s_r2[tid] = r2;
-  __syncthreads();
-  if (tid < N) {
-    double hu = 0.0, htu = 0.0;
-    for (int w = 0; w < nparts; ++w) {
-      hu += s_r1[w * N + tid];
-      htu += s_r2[w * N + tid];
-    }
-    s_hu[tid] = hu;
-    s_htu[tid] = htu;
-  }
-  __syncthreads();
-  if (tid < N) {
-    double b1 = 0.0, b2 = 0.0;
-    for (int jj = 0; jj < N; ++jj) {
-      b1 = fma(s_hu[jj], __ldg(p.D + tid * N + jj), b1);    // (hU) D^T
-      b2 = fma(s_htu[jj], __ldg(p.D + jj * N + tid), b2);   // (h^T U) D
-    }
-    p.B1[(size_t)blockIdx.x * N + tid] = b1;
-    p.B12[(size_t)blockIdx.x * N + tid] = b1 + b2;
-  }
-}
-
-// One-shot all-reduce over NVLink peer memory, fused into the last CTA of k_tail_row.
+// One-shot all-reduce over NVLink peer memory, fused into the last CTA of k_tail_reduce.
 // Every GPU owns a buffer  flags[2][world] | slots[2][world][stride]  that its peers map through
 // CUDA IPC.  Evaluation number `seq` (same on all ranks) uses parity seq&1:
 //   push   my (gradient | energy) vector into slot [parity][my_rank] of EVERY rank (remote stores)
@@ -255,169 +206,279 @@ constexpr int PEER_MAX = 8;
 struct PeerComm {
   double* slots[PEER_MAX];               // rank r's slot area (peer-mapped)
   unsigned long long* flags[PEER_MAX];   // rank r's flag area (peer-mapped)
-  int* error_flag;                       // set on wait time-out (never hang the GPU)
+  int* error_flag;                       // device flag, set on wait time-out (never hang the GPU);
+                                         // sticky: every later result is poisoned with NaN
+  int* error_flag_host;                  // same flag in mapped host memory (read by the C API)
+  unsigned long long timeout_ns;         // how long a rank waits for its peers
   unsigned long long* seq_ptr;           // device-resident evaluation counter (same on all ranks;
                                          // kept on the device so the launch can live in a CUDA graph)
   int rank, world, enabled;
   int stride;                            // doubles per slot (>= M*N+1)
 };
 
-struct TailParams {
-  PeerComm comm;
-  const double* T3;    // [nrows][Np^3]
-  const double* Gp;    // [Np^3][Np]: 2-RDM, a fastest (see k_prepare_gamma)
-  const double* U;     // [M][N]
-  const double* B1;    // [mloc][N]  one-body rows of the shard
-  const double* B12;   // [mloc][N]
-  double* out;         // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
-  double* rowE;        // [Np/AC][nrows] per-row energy partials
-  unsigned int* counter;
+constexpr int TAIL_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// Fused evaluation (see oo_k1.cuh): what runs before and after K1.
+// ---------------------------------------------------------------------------------------------
+
+// k_prepare_q — everything of an evaluation that depends on U but not on g:
+//   z = 0:  QA[p][a][e] = sum_c U[p][c] * G2A[c][a][e]     p in [0, M)
+//   z = 1:  QB[pl][a][e] = sum_c U[t0+pl][c] * G2B[c][a][e]  pl in [0, mloc)      (optional)
+//   z = 2:  one-body gradient rows of the shard (as k_onebody), one CTA per row
+// grid (ceil(Np^3 / 256), row chunks, 3), block 256.  A thread owns one (a, e) position, keeps its
+// N coefficients of G2 in registers and walks the rows of its chunk (coalesced 8-byte stores;
+// the row of U is a warp-wide broadcast load).
+struct PrepParams {
+  const double* U;      // [M][N]
+  const double* G2A;    // [Np][Np][Np^2]
+  const double* G2B;    // [Np][Np][Np^2] or NULL
+  double* QA;           // [M][Np][Np^2]
+  double* QB;           // [mloc][Np][Np^2]
+  const double* h;      // one-body part
+  const double* D;
+  double* B1;
+  double* B12;
   const int* done_flag;
-  int M, N, t0, mloc;  // shard: the one-body terms are added for rows in [t0, t0+mloc) only
-  int row0, nrows;
-  double two_body_grad_factor;  // 4 for the one-pass (V4-symmetric) gradient, 1 per generic slot
-  int accumulate;               // generic slots 1..3: out[x] += A[x], energy untouched
+  int M, N, t0, mloc;
+  int rows_per_chunk;
 };
 
-constexpr int TAIL_THREADS = 256;
-// Register blocking of the 2-RDM contraction: R rows x AC a-values per CTA (grid.y = Np / AC).
-// The 2-RDM is re-read from L2 once per CTA row-group and the T3 rows once per a-chunk, so the
-// L2 traffic is nrows/R * |Gp| + Np/AC * |T3|; R*AC accumulators live in registers.
-__host__ __device__ constexpr int tail_rows(int NT) { return NT <= 2 ? 4 : 8; }
-__host__ __device__ constexpr int tail_ac(int NT) { return NT >= 1 ? 8 : 8; }
-
-// grid (ceil(nrows / R), Np / AC), block 256.  For the R rows x and the AC values a of the CTA:
-//   A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                 (2-RDM contraction)
-//   out[x][a] = 4 A[x][a] + B12[x][a] (own rows),   rowE[y][x] = sum_a U[x][a] (A + B1)[x][a]
-// and the last CTA adds rowE in fixed order into out[M*N].
 template <int NT>
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
-  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32, R = tail_rows(NT),
-                AC = tail_ac(NT);
+__global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
+  constexpr int Np = NT * 8, Np2 = Np * Np, Np3 = Np2 * Np;
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ double s_part[NW][R][AC];
-  __shared__ double s_e[R][AC];
-  __shared__ double scratch[33];
-  __shared__ bool is_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int xl0 = blockIdx.x * R, a0 = blockIdx.y * AC, N = p.N;
-
-  double acc[R][AC];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int a = 0; a < AC; ++a) acc[r][a] = 0.0;
-  const double* tp[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) tp[r] = p.T3 + (size_t)min(xl0 + r, p.nrows - 1) * L;
-  // each thread takes two consecutive (j,e) positions per step: 16-byte loads everywhere
-#pragma unroll 2
-  for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
-    double2 tv[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) tv[r] = *reinterpret_cast<const double2*>(tp[r] + idx);
-    const double2* g0 = reinterpret_cast<const double2*>(p.Gp + (size_t)idx * Np + a0);
-    const double2* g1 = reinterpret_cast<const double2*>(p.Gp + (size_t)(idx + 1) * Np + a0);
-#pragma unroll
-    for (int a2 = 0; a2 < AC / 2; ++a2) {
-      const double2 u = __ldg(g0 + a2), v = __ldg(g1 + a2);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        acc[r][2 * a2] = fma(tv[r].x, u.x, fma(tv[r].y, v.x, acc[r][2 * a2]));
-        acc[r][2 * a2 + 1] = fma(tv[r].x, u.y, fma(tv[r].y, v.y, acc[r][2 * a2 + 1]));
+  const int tid = threadIdx.x, N = p.N, M = p.M;
+  if (blockIdx.z == 2) {
+    // ---- one-body rows: B1 = (h U D^T)[x], B12 = B1 + (h^T U D)[x] ----
+    const int ob = blockIdx.y * gridDim.x + blockIdx.x;
+    if (ob >= p.mloc) return;
+    __shared__ double s_r1[256], s_r2[256], s_hu[32], s_htu[32];
+    const int x = p.t0 + ob;
+    const int j = tid % N, part = tid / N, nparts = 256 / N;
+    double r1 = 0.0, r2 = 0.0;
+    if (part < nparts) {
+#pragma unroll 4
+      for (int q = part; q < M; q += nparts) {
+        const double u = __ldg(p.U + (size_t)q * N + j);
+        r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
+        r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
       }
     }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int a = 0; a < AC; ++a) {
-      double v = acc[r][a];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_part[warp][r][a] = v;
+    s_r1[tid] = r1;
+    s_r2[tid] = r2;
+    __syncthreads();
+    if (tid < N) {
+      double hu = 0.0, htu = 0.0;
+      for (int w = 0; w < nparts; ++w) {
+        hu += s_r1[w * N + tid];
+        htu += s_r2[w * N + tid];
+      }
+      s_hu[tid] = hu;
+      s_htu[tid] = htu;
     }
-  __syncthreads();
-  if (tid < R * AC) {
-    const int r = tid / AC, al = tid - r * AC, a = a0 + al;
-    const int xl = xl0 + r, x = p.row0 + xl;
-    double ev = 0.0;
-    if (xl < p.nrows && a < N) {
-      double av = 0.0;
+    __syncthreads();
+    if (tid < N) {
+      double b1 = 0.0, b2 = 0.0;
+      for (int jj = 0; jj < N; ++jj) {
+        b1 = fma(s_hu[jj], __ldg(p.D + tid * N + jj), b1);    // (hU) D^T
+        b2 = fma(s_htu[jj], __ldg(p.D + jj * N + tid), b2);   // (h^T U) D
+      }
+      p.B1[(size_t)ob * N + tid] = b1;
+      p.B12[(size_t)ob * N + tid] = b1 + b2;
+    }
+    return;
+  }
+  const bool second = blockIdx.z == 1;
+  if (second && p.G2B == nullptr) return;
+  const int idx = blockIdx.x * 256 + tid;             // (a, e) position
+  if (idx >= Np3) return;
+  const double* G2 = second ? p.G2B : p.G2A;
+  double coef[Np];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) av += s_part[w][r][al];
-      const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+  for (int c = 0; c < Np; ++c) coef[c] = __ldg(G2 + (size_t)c * Np3 + idx);
+  const int nrows = second ? p.mloc : M;
+  const int r0 = blockIdx.y * p.rows_per_chunk, r1 = min(nrows, r0 + p.rows_per_chunk);
+  double* out = (second ? p.QB : p.QA) + idx;
+  const double* Urow = p.U + (size_t)(second ? p.t0 : 0) * N;
+  for (int r = r0; r < r1; ++r) {
+    const double* u = Urow + (size_t)r * N;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < Np; ++c)
+      if (c < N) s = fma(__ldg(u + c), coef[c], s);
+    out[(size_t)r * Np3] = s;
+  }
+}
+
+// k_tail_reduce — what is left of an evaluation after K1: for every row x of U
+//   A[x][a] = sum over the streamed slabs that involve row x of their Aslab record, in fixed order
+//      own slabs (x, q)      record 0   (x in this GPU's shard)
+//      mirror slabs (t, x)   record 1   (t in the shard; pair mode: the selected pairs, t != x;
+//                                        generic mode: all t)
+//   out[x][a] = factor * A[x][a] + B12[x][a] (own rows),  rowE[x] = sum_a U[x][a] (A' + B1)[x][a]
+// then the last CTA adds rowE in fixed order into out[M*N], runs the one-shot all-reduce over
+// peer memory when attached and, inside oo_optimize, the optimiser transition itself (k_step's
+// body), so that one iteration is three launches: k_prepare_q, k1_half_transform, k_tail_reduce.
+// grid M rows (pair / generic) or mloc rows (dense), block 256 = (256 / Np) term groups x Np.
+struct TailReduceParams {
+  PeerComm comm;
+  const double* Aslab;   // [nslab][2][Np]
+  const int* rowstart;   // pair mode: [mloc] first slab of each row; NULL = dense slab order
+  const double* U;
+  const double* B1;
+  const double* B12;
+  double* out;
+  double* rowE;
+  unsigned int* counter;
+  const int* done_flag;
+  int M, N, t0, mloc;
+  int row0, nrows;
+  int mirror_mode;       // 0 none (dense V4), 1 pair-selected transposed tiles, 2 all t (generic)
+  int energy_mirror;     // 1: the mirror records enter the energy as well (V4: A is complete)
+  double grad_factor;    // 4 for the one-pass V4 gradient, 1 per generic slot pair
+  int accumulate;        // generic second pass: out += A, energy untouched
+  int do_step;           // run the optimiser transition in the last CTA
+  StepParams step;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReduceParams p) {
+  constexpr int Np = NT * 8, G = TAIL_THREADS / Np;
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  __shared__ double s_part[G][Np];
+  __shared__ double s_e[Np];
+  __shared__ bool is_last;
+  __shared__ StepSmem sm;
+  const int tid = threadIdx.x, a = tid % Np, grp = tid / Np, N = p.N, M = p.M;
+  const bool act = grp < G;                 // Np = 24: the last 16 threads have no group
+  const int x = p.row0 + blockIdx.x;
+  const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+  const int t1 = p.t0 + p.mloc;
+
+  // term lists in closed form (same enumeration as k_qcontract)
+  int n_own = 0, n_lo = 0, n_hi = 0, lo_first = 0, hi_first = 0, own_base = 0;
+  if (mine) {
+    n_own = p.rowstart ? pair_row_count(x, M) : M;
+    own_base = p.rowstart ? __ldg(p.rowstart + (x - p.t0)) : (x - p.t0) * M;
+  }
+  if (p.mirror_mode == 1) {
+    const int lo_end = min(x, t1);                       // t in [t0, lo_end), parity x&1
+    lo_first = p.t0 + (((x & 1) - (p.t0 & 1)) & 1);
+    n_lo = lo_end > lo_first ? (lo_end - lo_first + 1) >> 1 : 0;
+    const int hi_beg = max(x + 1, p.t0);                 // t in [hi_beg, t1), parity (x+1)&1
+    hi_first = hi_beg + ((((x + 1) & 1) - (hi_beg & 1)) & 1);
+    n_hi = t1 > hi_first ? (t1 - hi_first + 1) >> 1 : 0;
+  } else if (p.mirror_mode == 2) {
+    n_lo = p.mloc;                                       // slabs (t0 + i, x)
+  }
+  const int n_mir = n_lo + n_hi;
+  double s_own = 0.0, s_mir = 0.0;
+  for (int i = grp; act && i < n_own; i += G)
+    s_own += __ldcg(p.Aslab + ((size_t)(own_base + i) * 2) * Np + a);
+  for (int i = grp; act && i < n_mir; i += G) {
+    int slab;
+    if (p.mirror_mode == 1) {
+      const int t = i < n_lo ? lo_first + 2 * i : hi_first + 2 * (i - n_lo);
+      slab = __ldg(p.rowstart + (t - p.t0)) + pair_rank(t, x);
+    } else {
+      slab = i * M + x;
+    }
+    s_mir += __ldcg(p.Aslab + ((size_t)slab * 2 + 1) * Np + a);
+  }
+  // fixed-order sum over the groups: own part first, then the mirrored part
+  if (act) s_part[grp][a] = s_own;
+  __syncthreads();
+  double a_own = 0.0, a_mir = 0.0;
+  if (tid < Np) {
+#pragma unroll
+    for (int w = 0; w < G; ++w) a_own += s_part[w][tid];
+  }
+  __syncthreads();
+  if (act) s_part[grp][a] = s_mir;
+  __syncthreads();
+  if (tid < Np) {
+#pragma unroll
+    for (int w = 0; w < G; ++w) a_mir += s_part[w][tid];
+    double ev = 0.0;
+    if (tid < N) {
+      const double av = a_own + a_mir;
       double b1 = 0.0, b12 = 0.0;
       if (mine) {
-        b1 = p.B1[(size_t)(x - p.t0) * N + a];
-        b12 = p.B12[(size_t)(x - p.t0) * N + a];
+        b1 = p.B1[(size_t)(x - p.t0) * N + tid];
+        b12 = p.B12[(size_t)(x - p.t0) * N + tid];
       }
-      if (p.accumulate) p.out[(size_t)x * N + a] += p.two_body_grad_factor * av;
-      else p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
-      ev = __ldg(p.U + (size_t)x * N + a) * (av + b1);
+      if (p.accumulate) p.out[(size_t)x * N + tid] += p.grad_factor * av;
+      else p.out[(size_t)x * N + tid] = p.grad_factor * av + b12;
+      ev = __ldg(p.U + (size_t)x * N + tid) * ((p.energy_mirror ? av : a_own) + b1);
     }
-    s_e[r][al] = ev;
+    s_e[tid] = ev;
   }
   __syncthreads();
   if (tid == 0) {
-    for (int r = 0; r < R; ++r) {
-      if (xl0 + r < p.nrows) {
-        double e = 0.0;
-        for (int a = 0; a < AC; ++a) e += s_e[r][a];
-        p.rowE[(size_t)blockIdx.y * p.nrows + xl0 + r] = e;
-      }
-    }
+    double e = 0.0;
+    for (int i = 0; i < Np; ++i) e += s_e[i];
+    p.rowE[blockIdx.x] = e;
     __threadfence();
     const unsigned int prev = atomicAdd(p.counter, 1u);
-    is_last = (prev == (unsigned int)(gridDim.x * gridDim.y - 1));
+    is_last = (prev == (unsigned int)(gridDim.x - 1));
   }
   __syncthreads();
-  if (is_last) {
-    __threadfence();
+  if (!is_last) return;
+  __threadfence();
+  {
     double v = 0.0;
-    for (int i = tid; i < p.nrows * (int)gridDim.y; i += TAIL_THREADS)
-      v += ((volatile double*)p.rowE)[i];
-    v = block_sum(v, scratch);                  // fixed tree: deterministic
+    for (int i = tid; i < p.nrows; i += TAIL_THREADS) v += ((volatile double*)p.rowE)[i];
+    v = block_sum(v, sm.scratch);                  // fixed tree: deterministic
     if (tid == 0) {
-      if (!p.accumulate) p.out[(size_t)p.M * N] = v;
+      if (!p.accumulate) p.out[(size_t)M * N] = v;
       *p.counter = 0u;
     }
-    if (p.comm.enabled) {
-      // ---- fused one-shot all-reduce of out[0 .. M*N] over peer memory ----
-      __syncthreads();
-      const PeerComm& cm = p.comm;
-      const unsigned long long seq = *cm.seq_ptr + 1ull;
-      const int len = p.M * N + 1, par = (int)(seq & 1ull);
-      const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
-      for (int idx = tid; idx < len; idx += TAIL_THREADS) {
-        const double val = __ldcg(p.out + idx);
-        for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < cm.world)
-        *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = seq;
-      if (tid < cm.world) {
-        volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
-        const long long t_start = clock64();
-        while (*f < seq) {
-          if (clock64() - t_start > 4000000000ll) {   // ~2 s: give up instead of hanging
-            *cm.error_flag = 1;
-            break;
-          }
+  }
+  if (p.comm.enabled) {
+    // ---- fused one-shot all-reduce of out[0 .. M*N] over peer memory (see PeerComm) ----
+    __syncthreads();
+    const PeerComm& cm = p.comm;
+    const unsigned long long seq = *cm.seq_ptr + 1ull;
+    const int len = M * N + 1, par = (int)(seq & 1ull);
+    const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
+    for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+      const double val = __ldcg(p.out + idx);
+      for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < cm.world)
+      *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = seq;
+    if (tid < cm.world) {
+      volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
+      const unsigned long long t_start = global_timer_ns();
+      while (*f < seq) {
+        if (global_timer_ns() - t_start > cm.timeout_ns) {   // give up instead of hanging
+          *cm.error_flag = 1;
+          *((volatile int*)cm.error_flag_host) = 1;
+          break;
         }
       }
-      __threadfence_system();
-      __syncthreads();
-      const double* mine = cm.slots[cm.rank] + (size_t)par * cm.world * cm.stride;
-      for (int idx = tid; idx < len; idx += TAIL_THREADS) {
-        double s = 0.0;
-        for (int r = 0; r < cm.world; ++r) s += __ldcg(mine + (size_t)r * cm.stride + idx);
-        p.out[idx] = s;
-      }
-      __syncthreads();                 // everybody has read *seq_ptr
-      if (tid == 0) *cm.seq_ptr = seq;
     }
+    __threadfence_system();
+    __syncthreads();
+    // a time-out (now or earlier) means stale slots and ranks that no longer agree bit for
+    // bit: poison the result instead of returning a wrong one
+    const bool poisoned = *((volatile int*)cm.error_flag) != 0;
+    const double* mine_slots = cm.slots[cm.rank] + (size_t)par * cm.world * cm.stride;
+    for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+      double s = 0.0;
+      for (int r = 0; r < cm.world; ++r) s += __ldcg(mine_slots + (size_t)r * cm.stride + idx);
+      p.out[idx] = poisoned ? __longlong_as_double(0x7ff8000000000000ll) : s;
+    }
+    __syncthreads();                 // everybody has read *seq_ptr
+    if (tid == 0) *cm.seq_ptr = seq;
+  }
+  if (p.do_step) {
+    __threadfence();
+    __syncthreads();
+    opt_step_cta<TAIL_THREADS>(p.step, sm);
   }
 }
 

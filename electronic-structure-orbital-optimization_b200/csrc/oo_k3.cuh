@@ -121,11 +121,12 @@ __device__ inline void jacobi_eigh_smem(double* A, double* Q, double* cs, int n,
 // converges; quadratically once ||I - T|| < 1).  Only N x N products: ~3 us where the Jacobi
 // eigensolver needs ~100 us.  Returns false if 60 iterations did not reach ||I - T||_F < 1e-8
 // (then the caller falls back to the eigensolver).  All threads of the CTA must call.
+template <int THREADS>
 __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double* Z, double* W,
                                              int n, double* scratch, double* inv_sqrt_c,
                                              int* iters_out) {
   constexpr int LD = K3_NMAX + 1;
-  constexpr int EPT = (K3_NMAX * K3_NMAX + K3_THREADS - 1) / K3_THREADS;  // elements per thread
+  constexpr int EPT = (K3_NMAX * K3_NMAX + THREADS - 1) / THREADS;  // elements per thread
   const int tid = threadIdx.x, nth = blockDim.x, nn = n * n;
   if (tid < n) {
     double s = 0.0;
@@ -197,6 +198,7 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
 // U_out = orth(V) = V (V^T V)^(-1/2) for an M x N matrix V in global memory.  One CTA.  V and
 // U_out must be distinct buffers.  smem: sA, sB1, sB2, sB3 are K3_NMAX*(K3_NMAX+1) doubles each; cs 4*K3_NMAX;
 // scratch 32 doubles.
+template <int THREADS>
 __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
                                    double* sB1, double* sB2, double* sB3, double* cs,
                                    double* scratch, int* sflag, int* telemetry = nullptr,
@@ -241,7 +243,7 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
   double* S = sB2;  // inverse square root (up to `scale`) ends up here
   int ns_it = 0;
   const bool ok = !force_jacobi &&
-                  newton_schulz_invsqrt(sA, sB1, sB2, sB3, N, scratch, &scale, &ns_it);
+                  newton_schulz_invsqrt<THREADS>(sA, sB1, sB2, sB3, N, scratch, &scale, &ns_it);
   if (telemetry && tid == 0) {
     telemetry[0] += ns_it;
     if (!ok) telemetry[1] += 1;
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uo
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
       sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
-  retract_cta(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr, force_jacobi != 0);
+  retract_cta<K3_THREADS>(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
+                          force_jacobi != 0);
 }
 
 struct StepParams {
@@ -304,14 +307,21 @@ struct StepParams {
   int force_jacobi;     // debugging / testing: skip Newton-Schulz, use the eigensolver path
 };
 
+// Shared memory of one optimiser transition / retraction.
+struct StepSmem {
+  double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)], sB2[K3_NMAX * (K3_NMAX + 1)],
+      sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
+  int sflag;
+};
+
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
-__global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
-  __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
-      sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
-  __shared__ int sflag;
+// Called by every thread of ONE CTA of THREADS threads (the stand-alone k_step kernel, or the last
+// CTA of k_tail_reduce when the step is fused into the evaluation's tail).
+template <int THREADS>
+__device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
   OptState* st = p.st;
   if (st->done) return;
-  const int tid = threadIdx.x, nth = blockDim.x;
+  const int tid = threadIdx.x, nth = THREADS;
   const int MN = p.M * p.N;
   const int k = st->k;
   const double fk = p.gE[MN];
@@ -362,9 +372,9 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
       ug = fma(du, dg, ug);
       gg = fma(dg, dg, gg);
     }
-    uu = block_sum(uu, scratch);
-    ug = block_sum(ug, scratch);
-    gg = block_sum(gg, scratch);
+    uu = block_sum(uu, sm.scratch);
+    ug = block_sum(ug, sm.scratch);
+    gg = block_sum(gg, sm.scratch);
     alpha = (k & 1) ? uu / fabs(ug) : fabs(ug) / gg;
   }
   // ---- V = U_k - alpha G_k; shift histories ---------------------------------
@@ -375,8 +385,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
     p.Gprev[i] = g;
   }
   __syncthreads();
-  retract_cta(p.Vtmp, p.Ucur, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, &st->ns_iters,
-              p.force_jacobi != 0);
+  retract_cta<THREADS>(p.Vtmp, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3, sm.cs, sm.scratch,
+                       &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
@@ -384,6 +394,20 @@ __global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
     st->k = k + 1;
     if (!isfinite(alpha) || !isfinite(fk)) st->nan_flag = 1;
   }
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
+  __shared__ StepSmem sm;
+  opt_step_cta<K3_THREADS>(p, sm);
+}
+
+// Early stop requested by the host (a callback raised): behaves like the loop exit of the
+// reference at the current iteration (return value P4_array[0]).
+__global__ void k_force_stop(OptState* st) {
+  if (st->done) return;
+  st->done = 1;
+  st->k_final = st->k;
+  st->E_final = st->P4[0];
 }
 
 // Standalone BB update (compute_updated_partial_unitary, pupo.py:129-159) for API parity.
@@ -414,8 +438,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   }
   for (int i = tid; i < MN; i += nth) p.Vtmp[i] = p.Ucur[i] - alpha * p.Gcur[i];
   __syncthreads();
-  retract_cta(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
-              p.force_jacobi != 0);
+  retract_cta<K3_THREADS>(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
+                          p.force_jacobi != 0);
   if (tid == 0) *p.alpha_io = alpha;
 }
 

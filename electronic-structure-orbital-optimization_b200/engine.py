@@ -76,7 +76,7 @@ class OrbitalEngine:
         return out
 
     def _pad_g(self, g):
-        if self.M == self.M_user:
+        if self.M == self.M_user or tuple(g.shape) == (self.mloc,) + (self.M,) * 3:
             return g
         out = torch.zeros(self.mloc, self.M, self.M, self.M, dtype=torch.float64, device=g.device)
         out[:self.mloc_user, :self.M_user, :self.M_user, :self.M_user] = g
@@ -99,17 +99,32 @@ class OrbitalEngine:
         return float(out[0]), float(out[1])
 
     def set_integrals(self, h: torch.Tensor, g: torch.Tensor, assume_v4_symmetric: bool = False,
-                      sym_rtol: float = 1e-11, allow_generic: bool = True) -> None:
+                      sym_rtol: float = 1e-11, allow_generic: bool = True,
+                      g_pair_transposed: Optional[torch.Tensor] = None) -> None:
         """h [M,M]; g [mloc,M,M,M] (this shard's rows).  The tensors are used in place (no copy)
-        when already on the device, contiguous and M is even."""
+        when already on the device, contiguous and M is even.
+
+        `g_pair_transposed` [mloc,M,M,M] = g.permute(2,3,0,1)[t0:t0+mloc] of the FULL tensor selects
+        the generic (no permutational symmetry) path explicitly; a sharded engine needs it from
+        the caller because the rows of the transposed tensor live in other shards."""
         if tuple(h.shape) != (self.M_user, self.M_user):
             raise ValueError(f"h must be [{self.M_user},{self.M_user}], got {tuple(h.shape)}")
-        if tuple(g.shape) != (self.mloc_user,) + (self.M_user,) * 3:
+        padded = (self.mloc,) + (self.M,) * 3       # odd M: already zero-padded by the ingest
+        if tuple(g.shape) not in ((self.mloc_user,) + (self.M_user,) * 3, padded):
             raise ValueError(f"g must be [{self.mloc_user},{self.M_user},{self.M_user},"
                              f"{self.M_user}], got {tuple(g.shape)}")
         h = self._pad_h(_dev_f64(h, self.device))
         g = self._pad_g(_dev_f64(g, self.device))
         self.generic = False
+        if g_pair_transposed is not None:
+            if tuple(g_pair_transposed.shape) != (self.mloc_user,) + (self.M_user,) * 3:
+                raise ValueError("g_pair_transposed must have the shape of the g shard")
+            g_pt = self._pad_g(_dev_f64(g_pair_transposed, self.device))
+            self._keep["h"], self._keep["g"], self._keep["g_pt"] = h, g, g_pt
+            self._inputs_ready()
+            _lib.check(self.lib.oo_set_integrals_generic(self._ctx, _ptr(h), _ptr(g), _ptr(g_pt)))
+            self.generic = True
+            return
         if not assume_v4_symmetric:
             if self.mloc != self.M:
                 raise ValueError("a sharded g cannot be verified locally; verify the full tensor "
@@ -237,6 +252,11 @@ class OrbitalEngine:
         _lib.check(self.lib.oo_peer_attach(self._ctx, buf, rank, world))
         self.world = world
 
+    def set_peer_timeout(self, seconds: float) -> None:
+        """How long the fused all-reduce waits for a peer before it poisons the result (NaN) and
+        the next synchronous call raises (default 20 s)."""
+        _lib.check(self.lib.oo_set_peer_timeout_ms(self._ctx, float(seconds) * 1e3))
+
     def peer_status(self) -> int:
         rc = int(self.lib.oo_peer_status(self._ctx))
         if rc < 0:
@@ -262,15 +282,52 @@ class OrbitalEngine:
         grad = self._out[:MN].view(self.M, self.N)[:self.M_user].clone()
         return self._out[MN].clone(), grad
 
+    def _host_u(self, U) -> np.ndarray:
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        if self.M == self.M_user:
+            if U.shape != (self.M, self.N):
+                raise ValueError(f"U must be [{self.M_user},{self.N}], got {U.shape}")
+            return U
+        Uh = np.zeros((self.M, self.N), dtype=np.float64)
+        Uh[:self.M_user] = U
+        return Uh
+
     def energy_grad_host(self, U: np.ndarray):
         """Host-buffer entry point: (E float, dE/dU ndarray); H2D/D2H inside the call."""
-        Uh = np.zeros((self.M, self.N), dtype=np.float64)
-        Uh[:self.M_user] = np.asarray(U, dtype=np.float64)
+        Uh = self._host_u(U)
         E = C.c_double()
         grad = np.empty((self.M, self.N), dtype=np.float64)
         _lib.check(self.lib.oo_energy_grad_host(self._ctx, Uh.ctypes.data_as(C.c_void_p),
                                                 C.byref(E), grad.ctypes.data_as(C.c_void_p)))
         return float(E.value), grad[:self.M_user]
+
+    def submit_host(self, U: np.ndarray, slot: int) -> None:
+        """First half of a pipelined host-buffer evaluation (oo_eval_submit): returns at once."""
+        Uh = self._host_u(U)
+        _lib.check(self.lib.oo_eval_submit(self._ctx, Uh.ctypes.data_as(C.c_void_p), int(slot)))
+
+    def wait_host(self, slot: int, want_grad: bool = True):
+        """Second half (oo_eval_wait): (E float, dE/dU ndarray or None) of the slot."""
+        E = C.c_double()
+        grad = np.empty((self.M, self.N), dtype=np.float64) if want_grad else None
+        gp = grad.ctypes.data_as(C.c_void_p) if want_grad else C.c_void_p(0)
+        _lib.check(self.lib.oo_eval_wait(self._ctx, int(slot), C.byref(E), gp))
+        return float(E.value), (grad[:self.M_user] if want_grad else None)
+
+    def energies_host(self, Us) -> np.ndarray:
+        """Energies of a sequence of partial unitaries through the pipelined host-buffer path
+        (two slots in flight): what the finite-difference gradient of pupo.py:105-127 needs."""
+        out = np.empty(len(Us), dtype=np.float64)
+        pending = []
+        for i, U in enumerate(Us):
+            if len(pending) == 2:
+                j, s = pending.pop(0)
+                out[j] = self.wait_host(s, want_grad=False)[0]
+            self.submit_host(U, i & 1)
+            pending.append((i, i & 1))
+        for j, s in pending:
+            out[j] = self.wait_host(s, want_grad=False)[0]
+        return out
 
     def transform(self, U: torch.Tensor):
         """Rotated integrals (h' [N,N], g' [N,N,N,N]) on the device (shard-partial when sharded)."""
@@ -311,21 +368,40 @@ class OrbitalEngine:
     def optimize(self, U0, bb0: float, tol: float, maxiter: int, decay: float = 0.8,
                  callback=None):
         """The whole inner loop on the device.  Returns dict(U ndarray, energy, n_iter, E_hist,
-        stepsize).  `callback(iteration, energy)` is delivered live (at most 4 iterations late)
-        with the reference's arguments."""
-        cb_c = _lib.CALLBACK_T(lambda it, e, _u: callback(int(it), float(e))) if callback else \
-            C.cast(None, _lib.CALLBACK_T)
+        stepsize).  `callback(iteration, energy)` is delivered live (at most 4 iterations late,
+        after U has already advanced on the device) with the reference's arguments, on the
+        calling thread; an exception raised by it stops the device loop and is re-raised here.
+        With several GPUs a slow callback stalls this rank's enqueueing and therefore its peers
+        (they wait inside the fused all-reduce, see set_peer_timeout)."""
+        raised = []
+
+        def trampoline(it, e, _user):
+            # ctypes would print and swallow an exception raised here; keep it, ask the device
+            # loop to stop, and re-raise once oo_optimize has returned (the reference's callback
+            # exceptions leave compute_optimal_rotation, pupo.py:193-194)
+            if raised:
+                return
+            try:
+                callback(int(it), float(e))
+            except BaseException as exc:          # noqa: BLE001  (KeyboardInterrupt included)
+                raised.append(exc)
+                self.lib.oo_request_stop(self._ctx)
+
+        cb_c = _lib.CALLBACK_T(trampoline) if callback else C.cast(None, _lib.CALLBACK_T)
         _lib.check(self.lib.oo_set_callback(self._ctx, cb_c, None))
         Uh = np.zeros((self.M, self.N), dtype=np.float64)
         Uh[:self.M_user] = np.asarray(U0, dtype=np.float64)
         cap = max(int(maxiter), 0) + 8
         hist = np.zeros(cap, dtype=np.float64)
         n_iter, E, bb = C.c_int(), C.c_double(), C.c_double()
-        _lib.check(self.lib.oo_optimize(self._ctx, Uh.ctypes.data_as(C.c_void_p), float(bb0),
-                                        float(tol), int(maxiter), float(decay),
-                                        hist.ctypes.data_as(C.c_void_p), cap, C.byref(n_iter),
-                                        C.byref(E), C.byref(bb)))
-        _lib.check(self.lib.oo_set_callback(self._ctx, C.cast(None, _lib.CALLBACK_T), None))
+        rc = self.lib.oo_optimize(self._ctx, Uh.ctypes.data_as(C.c_void_p), float(bb0),
+                                  float(tol), int(maxiter), float(decay),
+                                  hist.ctypes.data_as(C.c_void_p), cap, C.byref(n_iter),
+                                  C.byref(E), C.byref(bb))
+        self.lib.oo_set_callback(self._ctx, C.cast(None, _lib.CALLBACK_T), None)
+        if raised:
+            raise raised[0]
+        _lib.check(rc)
         ns, jac = C.c_int(), C.c_int()
         _lib.check(self.lib.oo_retraction_stats(self._ctx, C.byref(ns), C.byref(jac)))
         return {"U": Uh[:self.M_user].copy(), "energy": float(E.value), "n_iter": int(n_iter.value),

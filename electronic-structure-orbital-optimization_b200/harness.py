@@ -91,12 +91,12 @@ def _rotated_spin_integrals(h: torch.Tensor, g: torch.Tensor, U: torch.Tensor, e
     (oo_transform) and is re-embedded into the reference's spin-block layout."""
     M, N = U.shape
     if engine is not None:
-        from . import ingest, synthetic
+        from . import ingest, rotated
+        if hasattr(engine, "_engine_for"):          # an esoo_b200 optimiser: its cached engine
+            return rotated.rotated_spin_integrals(engine, h, g, U)
         h_rot, g_rot = engine.transform(U)
         _, _, st = ingest.reduce_integrals(h, g)
-        pattern = "abba" if (0, 1, 1, 0) in st.blocks else "abab"
-        hs, gs = synthetic.spin_orbital_integrals(h_rot.cpu(), g_rot.cpu(), pattern)
-        return hs.numpy(), gs.numpy()
+        return rotated.expand_spin_blocks(h_rot, g_rot, st)
     W = torch.block_diag(U, U)
     h_rot = torch.einsum('pq,pi,qj->ij', h, W, W)
     g_rot = torch.einsum('pqrs,pi,qj,rk,sl->ijkl', g, W, W, W, W)

@@ -14,29 +14,71 @@ Differences, all deliberate:
   * `fun` is only *identified* (compute_rotated_energy / compute_rotated_weighted_energy_sum), not
     called; an arbitrary callable raises TypeError;
   * user callbacks are delivered in order and with the reference's arguments while the device
-    loop runs, at most one chunk (4 iterations) late (same (iteration, energy) pairs);
+    loop runs, at most one chunk (4 iterations) late and after U has already advanced on the
+    device (same (iteration, energy) pairs); an exception raised by the callback stops the device
+    loop and leaves compute_optimal_rotation, as in the reference;
   * instances hold no device handles, so `copy.deepcopy` (base_opt_orb_solver.py:75) is safe;
-    engines are cached in a module-level registry keyed by the integral tensors;
+    engines are cached in a module-level registry (see `_engine_for`; `clear_engine_cache()` frees
+    them -- a cached engine keeps its M^4 spatial tensor resident in HBM);
   * `inputs_on_host=True` (extension) makes `.device` report 'cpu' while the work still runs on
     the CUDA device: the outer loops move h, g and the RDMs to `optimizer.device` before every
     call (opt_orb_minimum_eigensolver.py:219-222), which for an 18.7 GB (2M)^4 tensor costs far
-    more than the optimisation itself; with host inputs a cache hit touches 1 % of the tensor.
+    more than the optimisation itself;
+  * multi-GPU (extension): when torch.distributed is initialised with more
+    than one rank (one process per GPU) every rank calls compute_optimal_rotation with the same
+    arguments; each keeps only its rows of the first ERI index (pair-packed when the tensor is
+    V4-symmetric), the library all-reduces the M*N+1 doubles per evaluation (fused into the tail
+    kernel over NVLink peer memory, NCCL otherwise) and every rank returns the same U.
+    `distributed=False` switches it off;
+  * `two_body_integrals` may be an `esoo_b200.SpatialIntegrals` (already spatial, possibly an
+    already sharded / pair-packed device tensor): the only way to express problems whose (2M)^4
+    spin-orbital tensor cannot exist (BASELINE.json configs 4 and 5).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Optional, Tuple
 
 import numpy as np
 import torch
 
+from . import distributed as dist_mod
 from . import ingest
 from .engine import OrbitalEngine
 
 _RECOGNISED = ("compute_rotated_energy", "compute_rotated_weighted_energy_sum")
 
-# (device index, data_ptr, _version, shape) of the two-body tensor -> (engine, structure)
+# content key -> _CacheEntry
 _ENGINE_CACHE = {}
 _ENGINE_CACHE_MAX = 2
+# (device index, M, N) -> OrbitalEngine without integrals: serves orth() / BB updates
+_LIGHT_ENGINES = {}
+
+
+class _CacheEntry:
+    __slots__ = ("engine", "structure", "g_ref", "g_version", "h_ref", "h_version")
+
+    def __init__(self, engine, structure, g, h):
+        self.engine, self.structure = engine, structure
+        self.g_ref, self.g_version = _weak(g), _version(g)
+        self.h_ref, self.h_version = _weak(h), _version(h)
+
+    def same_objects(self, g, h) -> bool:
+        """The very tensors this engine was built from, unmodified since (autograd version
+        counter): a hit that does not have to look at the data."""
+        return self.g_ref is not None and self.g_ref() is g and _version(g) == self.g_version \
+            and self.h_ref is not None and self.h_ref() is h and _version(h) == self.h_version
+
+
+def _weak(t):
+    try:
+        return weakref.ref(t)
+    except TypeError:
+        return None
+
+
+def _version(t) -> int:
+    return int(getattr(t, "_version", 0))
 
 
 def _fun_identity(fun) -> Tuple[str, object]:
@@ -54,9 +96,36 @@ def _fun_identity(fun) -> Tuple[str, object]:
 
 
 def clear_engine_cache() -> None:
-    for eng, _ in _ENGINE_CACHE.values():
-        eng.close()
+    """Destroy every cached engine (and release the ERI tensors they keep resident in HBM)."""
+    for entry in _ENGINE_CACHE.values():
+        entry.engine.close()
     _ENGINE_CACHE.clear()
+    for eng in _LIGHT_ENGINES.values():
+        eng.close()
+    _LIGHT_ENGINES.clear()
+
+
+def _weights(n: int, seed: int, device) -> torch.Tensor:
+    gen = torch.Generator().manual_seed(seed)
+    return (torch.rand(n, generator=gen, dtype=torch.float64) + 0.5).to(device)
+
+
+def content_checksum(t: torch.Tensor, sample: bool = False) -> Tuple[float, float]:
+    """Fingerprint of a tensor computed where it lives.  Full mode: a bilinear form w1^T T w2 with
+    fixed pseudo-random positive weights over the tensor seen as a [n0, rest] matrix (one streaming
+    pass; any single-element change and any permutation of entries changes it) plus sum |t|.
+    Sample mode (opt-in, for huge host tensors): the same on a 1 % strided sample -- a changed
+    tensor that agrees on the sample is NOT detected."""
+    flat = t.reshape(-1)
+    if sample:
+        flat = flat[::101]
+        w = _weights(flat.numel(), 7, flat.device)
+        return float(torch.dot(flat, w)), float(flat.abs().sum())
+    n0 = t.shape[0]
+    mat = t.reshape(n0, -1)
+    w2 = _weights(mat.shape[1], 11, t.device)
+    w1 = _weights(n0, 13, t.device)
+    return float(torch.dot(torch.mv(mat, w2), w1)), float(flat.abs().sum())
 
 
 class PartialUnitaryProjectionOptimizer:
@@ -71,12 +140,16 @@ class PartialUnitaryProjectionOptimizer:
                  decay_factor: float = 0.8,
                  gradient_method: Optional[str] = 'autograd',
                  device: Optional[str] = 'cuda',
-                 inputs_on_host: bool = False) -> None:
+                 inputs_on_host: bool = False,
+                 distributed: Optional[bool] = None,
+                 cache_check: str = 'full') -> None:
         if gradient_method not in ('autograd', 'finite_difference'):
             raise ValueError("gradient_method must be 'autograd' or 'finite_difference'")
         if not str(device).startswith('cuda'):
             raise ValueError("this implementation runs on CUDA devices only (device='cuda[:n]'); "
                              "use the reference class for device='cpu'")
+        if cache_check not in ('full', 'sample', 'off'):
+            raise ValueError("cache_check must be 'full', 'sample' or 'off'")
         self._callback = callback
         self.stopping_tolerance = stopping_tolerance
         self.maxiter = maxiter
@@ -86,6 +159,12 @@ class PartialUnitaryProjectionOptimizer:
         # what the outer loops read to decide where to put the tensors they pass in
         self.device = 'cpu' if inputs_on_host else device
         self.gradient_method = gradient_method
+        # None: shard over the ranks of torch.distributed when it is initialised with world > 1
+        self.distributed = distributed
+        # 'full': content-keyed engine cache verified by a checksum of the whole tensor;
+        # 'sample': 1 % strided sample (cheap for host tensors, can miss a change);
+        # 'off': no content caching (an engine is rebuilt unless the same tensor objects return)
+        self.cache_check = cache_check
         self.last_result = None      # bookkeeping of the most recent compute_optimal_rotation
 
     # -- properties of the reference (pupo.py:50-68) -------------------------------------------
@@ -110,35 +189,136 @@ class PartialUnitaryProjectionOptimizer:
         d = torch.device(self.compute_device)
         return torch.device('cuda', d.index if d.index is not None else torch.cuda.current_device())
 
-    def _engine_for(self, one_body_integrals: torch.Tensor, two_body_integrals: torch.Tensor):
+    def _ranks(self) -> Tuple[int, int]:
+        """(rank, world) of the sharded run, (0, 1) when not distributed."""
+        import torch.distributed as dist
+        if self.distributed is False or not dist.is_available() or not dist.is_initialized():
+            if self.distributed:
+                raise RuntimeError("distributed=True needs an initialised torch.distributed")
+            return 0, 1
+        return dist.get_rank(), dist.get_world_size()
+
+    def _attach(self, eng: OrbitalEngine, world: int) -> None:
+        if world > 1:
+            dist_mod.attach_nccl(eng)
+            try:
+                dist_mod.attach_peer_memory(eng)       # all-reduce fused into the tail kernel
+            except Exception:                           # no peer access: NCCL serves the all-reduce
+                pass
+
+    def _engine_from_spatial(self, h: torch.Tensor, sp: "ingest.SpatialIntegrals", rank, world):
         dev = self._torch_device()
-        # The outer loops re-create the device tensors every iteration (.to(device) / .to('cpu'),
-        # opt_orb_minimum_eigensolver.py:219-235), so identity is useless as a key: use a content
-        # fingerprint computed WHERE THE TENSOR LIVES, so that a cache hit costs neither an H2D copy
-        # of the (2M)^4 tensor nor a re-ingest.  Device tensors: full sums (one streaming pass);
-        # host tensors: a 1 % strided sample plus the one-body sum.
-        g_src, h_src = two_body_integrals, one_body_integrals
-        flat = g_src.reshape(-1)
-        if g_src.is_cuda:
-            fp = (float(flat.sum()), float(flat[::7].sum()), float(flat.abs().max()))
+        if world > 1 and sp.mloc == sp.M:
+            raise ValueError("SpatialIntegrals of a multi-rank run must hold this rank's shard "
+                             "(t0, mloc from esoo_b200.shard_range)")
+        eng = OrbitalEngine(sp.M, self._n_active, device=dev, t0=sp.t0, mloc=sp.mloc)
+        if sp.packed:
+            eng.set_integrals_packed(h, sp.g)
+        elif sp.v4_symmetric:
+            eng.set_integrals(h, sp.g, assume_v4_symmetric=True)
         else:
-            sample = flat[::101]
-            fp = (float(sample.sum()), float(sample.abs().sum()), float(flat[-1]))
-        key = (dev.index, str(g_src.device.type), tuple(g_src.shape), self._n_active, fp,
-               float(h_src.sum()))
-        hit = _ENGINE_CACHE.get(key)
-        if hit is not None:
-            return hit
-        h_dev, g_dev = one_body_integrals.to(dev), two_body_integrals.to(dev)
-        h_sp, g_sp, structure = ingest.reduce_integrals_device(h_dev, g_dev)
-        del g_dev
+            eng.set_integrals(h, sp.g, g_pair_transposed=sp.g_pair_transposed)
+        self._attach(eng, world)
+        return eng, sp.structure
+
+    def _engine_from_spin(self, h_src: torch.Tensor, g_src: torch.Tensor, rank: int, world: int):
+        """Spin-orbital tensors (host or device) -> engine holding this rank's rows of the spatial
+        block; the M^4 spatial tensor is only materialised on a single-GPU run."""
+        import torch.distributed as dist
+        dev = self._torch_device()
+        P = g_src.shape[0]
+        M = P // 2
+        t0, mloc = dist_mod.shard_range(M, rank, world)
+        if world == 1:
+            h_dev, g_dev = h_src.to(dev), g_src.to(dev)
+            h_sp, g_sp, structure = ingest.reduce_integrals_device(h_dev, g_dev, pad_even=True)
+            del g_dev
+            eng = OrbitalEngine(M, self._n_active, device=dev)
+            eng.set_integrals(h_sp, g_sp)               # verifies V4 on the device; generic else
+            return eng, structure
+        # ---- sharded: every rank reads only its rows --------------------------------------
+        if g_src.is_cuda:
+            h_sp, g_rows, structure = ingest.reduce_integrals_device(h_src.to(dev), g_src.to(dev),
+                                                                     t0=t0, mloc=mloc,
+                                                                     pad_even=True)
+        else:
+            h_sp, g_rows, structure = ingest.reduce_integrals_rows_host(h_src, g_src, t0, mloc)
+            g_rows = g_rows.to(dev)
+        mask = torch.tensor([ingest.block_mask(structure)], dtype=torch.int64,
+                            device=dev if dist.get_backend() == "nccl" else "cpu")
+        lo, hi = mask.clone(), mask.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if int(lo.item()) != int(hi.item()):
+            raise NotImplementedError("the ranks see different non-zero spin blocks of g")
+        ref_block = structure.blocks[0] if structure.blocks else (0, 0, 0, 0)
+        asym, gmax = ingest.v4_asymmetry_rows(g_src, M, ref_block, t0, mloc)
+        flag = torch.tensor([1 if asym <= 1e-11 * max(gmax, 1e-300) else 0], dtype=torch.int64,
+                            device=mask.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        eng = OrbitalEngine(M, self._n_active, device=dev, t0=t0, mloc=mloc)
+        if int(flag.item()) == 1:
+            if M % 2 == 0:
+                packed = eng.pack_pair_slabs(g_rows)    # half the residency, same traffic
+                del g_rows
+                eng.set_integrals_packed(h_sp, packed)
+            else:
+                eng.set_integrals(h_sp, g_rows, assume_v4_symmetric=True)
+        else:
+            blk = ingest._blk(g_src, M, ref_block)
+            g_pt = blk.permute(2, 3, 0, 1)[t0:t0 + mloc].contiguous().to(dev)
+            eng.set_integrals(h_sp, g_rows, g_pair_transposed=g_pt)
+        self._attach(eng, world)
+        return eng, structure
+
+    def _engine_for(self, one_body_integrals: torch.Tensor, two_body_integrals):
+        """The engine that holds these integrals, from the module-level cache when possible.
+
+        The outer loops re-create the device tensors every iteration (.to(device) / .to('cpu'),
+        opt_orb_minimum_eigensolver.py:219-235), so object identity alone is not enough:
+          1. same tensor objects, unmodified (weak reference + autograd version counter): hit
+             without touching the data (host tensors with inputs_on_host=True take this path);
+          2. otherwise a content checksum computed where the tensor lives (cache_check='full': one
+             streaming pass over the whole tensor; 'sample': 1 % of it; 'off': never)."""
+        dev = self._torch_device()
+        rank, world = self._ranks()
+        g_src, h_src = two_body_integrals, one_body_integrals
+        spatial = isinstance(g_src, ingest.SpatialIntegrals)
+        g_key_t = g_src.g if spatial else g_src
+        for entry in _ENGINE_CACHE.values():
+            if entry.same_objects(g_key_t, h_src) and entry.engine.N == self._n_active and \
+                    entry.engine.device == dev:
+                return entry.engine, entry.structure
+        key = None
+        if self.cache_check != 'off':
+            sample = self.cache_check == 'sample'
+            key = (dev.index, rank, world, str(g_key_t.device.type), tuple(g_key_t.shape),
+                   self._n_active, spatial and (g_src.t0, g_src.mloc, g_src.packed, g_src.pattern),
+                   content_checksum(g_key_t, sample), content_checksum(h_src, False))
+            hit = _ENGINE_CACHE.get(key)
+            if hit is not None:
+                hit.g_ref, hit.g_version = _weak(g_key_t), _version(g_key_t)
+                hit.h_ref, hit.h_version = _weak(h_src), _version(h_src)
+                return hit.engine, hit.structure
         while len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
             old_key = next(iter(_ENGINE_CACHE))
-            _ENGINE_CACHE.pop(old_key)[0].close()
-        eng = OrbitalEngine(structure.M, self._n_active, device=dev)
-        eng.set_integrals(h_sp, g_sp)
-        _ENGINE_CACHE[key] = (eng, structure)
+            _ENGINE_CACHE.pop(old_key).engine.close()
+        if spatial:
+            eng, structure = self._engine_from_spatial(h_src, g_src, rank, world)
+        else:
+            eng, structure = self._engine_from_spin(h_src, g_src, rank, world)
+        _ENGINE_CACHE[key if key is not None else ("id", id(g_key_t), id(h_src))] = \
+            _CacheEntry(eng, structure, g_key_t, h_src)
         return eng, structure
+
+    def _light_engine(self, M: int, N: int) -> OrbitalEngine:
+        """A context without integrals (a few small buffers): retraction / BB update only."""
+        dev = self._torch_device()
+        key = (dev.index, int(M), int(N))
+        eng = _LIGHT_ENGINES.get(key)
+        if eng is None:
+            eng = _LIGHT_ENGINES[key] = OrbitalEngine(M, N, device=dev)
+        return eng
 
     def _prepare(self, fun, oneRDM, twoRDM, one_body_integrals, two_body_integrals, n_active: int):
         name, owner = _fun_identity(fun)
@@ -174,12 +354,8 @@ class PartialUnitaryProjectionOptimizer:
     # -- methods of the reference --------------------------------------------------------------
     def orth(self, V: torch.Tensor) -> torch.Tensor:
         """orth(V) = V (V^T V)^(-1/2) (pupo.py:70-83), computed by the CUDA retraction kernel."""
-        dev = self._torch_device()
-        eng = OrbitalEngine(V.shape[0], V.shape[1], device=dev)
-        try:
-            return eng.orth(V.to(dev)).clone()
-        finally:
-            eng.close()
+        eng = self._light_engine(V.shape[0], V.shape[1])
+        return eng.orth(V.to(eng.device)).clone()
 
     def _bound_problem(self, func):
         """Recover (fun, oneRDM, twoRDM, h, g) from the functools.partial the reference builds
@@ -199,6 +375,22 @@ class PartialUnitaryProjectionOptimizer:
         eng = self._prepare(fun, d, g2, h, g, partial_unitary.shape[1])
         return eng.energy_grad(partial_unitary)[1]
 
+    @staticmethod
+    def _fd_gradient(eng: OrbitalEngine, U: np.ndarray) -> np.ndarray:
+        """Central differences, step 1e-8 per entry (pupo.py:113-125): the 2*M*N energies go
+        through the pipelined host-buffer path of the library (two evaluations in flight)."""
+        step = 10 ** -8
+        M, N = U.shape
+        trial = []
+        for i in range(M):
+            for j in range(N):
+                up, um = U.copy(), U.copy()
+                up[i, j] += step
+                um[i, j] -= step
+                trial.extend((up, um))
+        E = eng.energies_host(trial)
+        return ((E[0::2] - E[1::2]) / (2 * step)).reshape(M, N)
+
     def compute_rotated_energy_gradient(self, partial_unitary: torch.Tensor,
                                         func: Callable) -> torch.Tensor:
         """Central finite-difference gradient, step 1e-8 (pupo.py:105-127), each of the 2*M*N
@@ -206,15 +398,7 @@ class PartialUnitaryProjectionOptimizer:
         fun, d, g2, h, g = self._bound_problem(func)
         eng = self._prepare(fun, d, g2, h, g, partial_unitary.shape[1])
         U = partial_unitary.detach().to('cpu').numpy().astype(np.float64)
-        out = np.empty_like(U)
-        step = 10 ** -8
-        for i in range(U.shape[0]):
-            for j in range(U.shape[1]):
-                up, um = U.copy(), U.copy()
-                up[i, j] += step
-                um[i, j] -= step
-                out[i, j] = (eng.energy_grad_host(up)[0] - eng.energy_grad_host(um)[0]) / (2 * step)
-        return torch.from_numpy(out).to(self._torch_device())
+        return torch.from_numpy(self._fd_gradient(eng, U)).to(self._torch_device())
 
     def compute_updated_partial_unitary(self, iteration_number: int,
                                         current_partial_unitary: torch.Tensor,
@@ -224,17 +408,13 @@ class PartialUnitaryProjectionOptimizer:
                                         ) -> torch.Tensor:
         """BB step size update + retraction (pupo.py:129-159); mutates BBstepsize like the
         reference."""
-        dev = self._torch_device()
         M, N = current_partial_unitary.shape
-        eng = OrbitalEngine(M, N, device=dev)
-        try:
-            U_next, step = eng.bb_update(iteration_number, current_partial_unitary,
-                                         previous_partial_unitary, current_rotated_energy_gradient,
-                                         previous_rotated_energy_gradient, float(self._BBstepsize))
-            self._BBstepsize = step
-            return U_next.clone()
-        finally:
-            eng.close()
+        eng = self._light_engine(M, N)
+        U_next, step = eng.bb_update(iteration_number, current_partial_unitary,
+                                     previous_partial_unitary, current_rotated_energy_gradient,
+                                     previous_rotated_energy_gradient, float(self._BBstepsize))
+        self._BBstepsize = step
+        return U_next.clone()
 
     def compute_optimal_rotation(self, fun: Callable,
                                  initial_partial_unitary: torch.Tensor,
@@ -264,21 +444,13 @@ class PartialUnitaryProjectionOptimizer:
     def _optimal_rotation_finite_difference(self, eng: OrbitalEngine, U0: np.ndarray):
         """gradient_method='finite_difference' parity mode: the reference's driver with the
         finite-difference gradient; energies from the CUDA path, loop on the host."""
-        step = 10 ** -8
-
         def energy(U):
             return eng.energy_grad_host(U)[0]
 
         def grad(U):
-            out = np.empty_like(U)
-            for i in range(U.shape[0]):
-                for j in range(U.shape[1]):
-                    up, um = U.copy(), U.copy()
-                    up[i, j] += step
-                    um[i, j] -= step
-                    out[i, j] = (energy(up) - energy(um)) / (2 * step)
-            return out
+            return self._fd_gradient(eng, U)
 
+        light = self._light_engine(eng.M_user, eng.N)
         dev = eng.device
         tol, d = self.stopping_tolerance, self.decay_factor
         P4, St = [None, None, None], [None, 1.5 * tol]
@@ -288,8 +460,8 @@ class PartialUnitaryProjectionOptimizer:
         def advance():
             nonlocal U_cur, U_prev, G_cur, G_prev, k
             t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-            U_new, bb = eng.bb_update(k, t(U_cur), t(U_prev), t(G_cur), t(G_prev),
-                                      float(self._BBstepsize))
+            U_new, bb = light.bb_update(k, t(U_cur), t(U_prev), t(G_cur), t(G_prev),
+                                        float(self._BBstepsize))
             self._BBstepsize = bb
             U_new = U_new.cpu().numpy()
             G_new = grad(U_new)

@@ -90,11 +90,15 @@ int oo_set_integrals(oo_ctx* ctx, const double* h_dev, const double* g_dev, unsi
  *     base.py:89-90). */
 int oo_pair_slab_list(int M, int t0, int mloc, int* tq_host, int capacity);
 int oo_pack_pair_slabs(oo_ctx* ctx, const double* g_dense_dev, double* g_packed_dev);
-/* Two-body tensors WITHOUT V4 symmetry (single GPU only): registers g_dev [M]^4 and its
- * pair-transposed copy g_pt_dev[r][s][p][q] = g[p][q][r][s].  Every evaluation then makes two dense
- * passes (one per tensor) and builds dE/dU from the four index-slot terms, with the 2-RDM used as
- * given (no symmetrisation).  Four times the work of the symmetric path; completes the contract
- * of compute_rotated_energy for arbitrary real tensors (base.py:534-563, pupo.py:85-103). */
+/* Two-body tensors WITHOUT V4 symmetry: registers this GPU's shard of g, g_dev [mloc][M][M][M]
+ * (rows t0.. of the FIRST index), and the same rows of the pair-transposed tensor,
+ * g_pt_dev[r][s][p][q] = g[p][q][r][s] for r in [t0, t0+mloc) (i.e. the shard of g's THIRD index,
+ * stored with that index first).  Every evaluation then makes two dense passes (one per tensor)
+ * and builds dE/dU from the four index-slot terms, with the 2-RDM used as given (no
+ * symmetrisation): rows t and q of dE/dU come from the first pass, rows r and s from the second,
+ * every GPU contributes partial rows for all of U and the usual all-reduce completes them.  Four
+ * times the work of the symmetric path; completes the contract of compute_rotated_energy for
+ * arbitrary real tensors (base.py:534-563, pupo.py:85-103). */
 int oo_set_integrals_generic(oo_ctx* ctx, const double* h_dev, const double* g_dev,
                              const double* g_pt_dev);
 /* Max |g - g∘pi| over the three V4 permutations and max |g| of a FULL (unsharded) device tensor
@@ -114,6 +118,13 @@ int oo_set_rdms(oo_ctx* ctx, const double* D_dev, const double* G_dev);
  * OO_ERR_UNSUPPORTED when the blocks differ (unrestricted integrals). */
 int oo_ingest_spin_g(int device, const double* g_spin_dev, int M, double rtol,
                      double* g_sp_out_dev, unsigned* block_mask, double* stats_host);
+/* The same for one shard: only rows [t0, t0+mloc) of the first index of the spatial block are
+ * extracted (and compared across the non-zero spin blocks), into g_out_dev [mloc][Mpad][Mpad][Mpad]
+ * with Mpad >= M (Mpad = M+1 pads an odd M to the even extent oo_create needs; the padding must
+ * be zero on entry).  A rank of a multi-GPU run never materialises the M^4 spatial tensor. */
+int oo_ingest_spin_g_rows(int device, const double* g_spin_dev, int M, double rtol, int t0,
+                          int mloc, int Mpad, double* g_out_dev, unsigned* block_mask,
+                          double* stats_host);
 /* RDMs straight from the reference's spin-orbital tensors (base.py:362-532 layout): nstates (<=8)
  * device tensors D_n [2N][2N], G_n [2N]^4 given as HOST arrays of device pointers, host weights
  * (NULL = 1): D~ = sum_n w_n (D_n[aa] + D_n[bb]), G~ = sum_n w_n sum_{b in block_mask} G_n[block b]
@@ -148,6 +159,15 @@ int oo_energy_grad_allreduce(oo_ctx* ctx, const double* U_dev, double* out_dev);
 /* Same through host buffers: H2D of U, evaluation, all-reduce when a communicator is attached,
  * D2H of E and dE/dU, synchronous.  This is the reference-facing call used for end-to-end timing. */
 int oo_energy_grad_host(oo_ctx* ctx, const double* U_host, double* E_host, double* grad_host);
+/* The same call split in two so that host-buffer evaluations can be pipelined (two slots, 0 and
+ * 1): oo_eval_submit copies U_host into pinned memory and enqueues H2D (own copy stream),
+ * evaluation (+ all-reduce) and D2H (own copy stream) without waiting; oo_eval_wait blocks until
+ * the slot's result has landed and hands it out (grad_host may be NULL).  Submitting slot s+1 before
+ * waiting for slot s overlaps the copies and the host work of one evaluation with the kernels of
+ * the next; the finite-difference gradient (pupo.py:105-127: 2*M*N energies) and bench.py's
+ * end-to-end leg use it.  oo_energy_grad_host = submit + wait on slot 0. */
+int oo_eval_submit(oo_ctx* ctx, const double* U_host, int slot);
+int oo_eval_wait(oo_ctx* ctx, int slot, double* E_host, double* grad_host);
 /* Rotated integrals h' [N][N], g' [N][N][N][N] (this shard's partial sum over the first index).
  * Replaces the tensor part of get_rotated_hamiltonian, base.py:597-604, and
  * opt_orb_mcvqe.py:90-98. */
@@ -172,6 +192,10 @@ int oo_bb_update(oo_ctx* ctx, int iteration, const double* U_cur_dev, const doub
  * device keeps iterating.  NULL disables it. */
 typedef void (*oo_callback_t)(int iteration, double energy, void* user);
 int oo_set_callback(oo_ctx* ctx, oo_callback_t cb, void* user);
+/* May be called from inside a callback: the running oo_optimize stops as if the reference's loop
+ * had ended at the iteration the device has reached (it returns OO_OK with that iterate).  Used by
+ * the Python mirror to propagate an exception raised by the user's callback. */
+int oo_request_stop(oo_ctx* ctx);
 int oo_optimize(oo_ctx* ctx, double* U_io_host, double bb0, double tol, int maxiter, double decay,
                 double* E_hist_host, int hist_cap, int* n_iter, double* E_final,
                 double* bb_final);
@@ -192,12 +216,19 @@ int oo_allreduce(oo_ctx* ctx, double* buf_dev, size_t count);
 int oo_peer_export(oo_ctx* ctx, void* handle64_host);
 int oo_peer_attach(oo_ctx* ctx, const void* handles_host, int rank, int world);
 int oo_peer_status(oo_ctx* ctx);
+/* How long a rank waits for its peers inside the fused all-reduce (default 20 s, or the
+ * environment variable OO_PEER_TIMEOUT_MS).  On a time-out the result of that and of every later
+ * evaluation is NaN on the device and oo_optimize / oo_energy_grad_host / oo_eval_wait /
+ * oo_synchronize return OO_ERR_NCCL: a stalled peer can never turn into a silently wrong
+ * gradient.  Host callbacks run on the enqueueing thread and can stall the peers for as long
+ * as they take. */
+int oo_set_peer_timeout_ms(oo_ctx* ctx, double milliseconds);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
-/* Average device time (ms) of the kernels of the last oo_energy_grad call, measured with CUDA
- * events on the context stream: [0] K1 half-transform, [1] q-contraction, [2] row tail (2-RDM
- * contraction + one-body terms + energy), [3] reserved (0), [4] whole evaluation.  Requires
- * oo_set_timing(ctx,1) beforehand. */
+/* Device time (ms) of the kernels of the last oo_energy_grad call, measured with CUDA events on
+ * the context stream: [0] K1 half-transform with the fused 2-RDM contraction, [1] k_prepare_q
+ * (Q tensors + one-body rows), [2] k_tail_reduce (row sums, energy, all-reduce), [3] reserved
+ * (0), [4] whole evaluation.  Requires oo_set_timing(ctx,1) beforehand. */
 int oo_set_timing(oo_ctx* ctx, int enable);
 int oo_last_timing(oo_ctx* ctx, float* ms5_host);
 /* Number of kernels launched by this context since creation. */

@@ -38,7 +38,14 @@ CASES = [
     ("abba_M12_N4", 12, 4, "abba", 1, None, True, (0.02, 1e-8, 500), True, 1.0),
     ("cfg1_M28_N2", 28, 2, "abba", 1, None, True, (0.02, 1e-8, 150), False, 1.0),
     ("cfg3_M20_N2_k3", 20, 2, "abba", 3, [3, 2, 1], True, (0.02, 1e-8, 150), False, 1.0),
-    ("cfg2_M56_N4", 56, 4, "abba", 1, None, False, None, False, 1.0),
+    ("cfg2_M56_N4", 56, 4, "abba", 1, None, True, (0.02, 1e-8, 150), False, 1.0),
+]
+
+# BASELINE.json config 3 at its true shape (H2 cc-pV5Z: M=110 spatial -> 4 spin orbitals, 3
+# state-averaged RDMs, weights [3,2,1]): an 18.7 GB spin-orbital tensor, run only on request
+# (`make_golden.py big`, ~25 GB of host memory, a few minutes).
+BIG_CASES = [
+    ("cfg3_M110_N2_k3", 110, 2, "abba", 3, [3, 2, 1], True, (0.02, 1e-8, 40), False, 1.0),
 ]
 
 
@@ -55,9 +62,11 @@ def build_inputs(M, N, pattern, n_states, seed_shift=0, g_scale=1.0):
     return hs, gs, Ds, Gs, U0
 
 
-def main():
+def main(cases=None, only=None):
     Pupo, _ = ref_loader.load_reference()
-    for (name, M, N, pattern, k, weights, run_opt, optp, store, g_scale) in CASES:
+    for (name, M, N, pattern, k, weights, run_opt, optp, store, g_scale) in (cases or CASES):
+        if only and name not in only:
+            continue
         hs, gs, Ds, Gs, U0 = build_inputs(M, N, pattern, k, g_scale=g_scale)
         solver = ref_loader.make_solver(True, weights)
         if weights is None:
@@ -234,7 +243,58 @@ def main_decay():
     np.savez_compressed(os.path.join(HERE, "opt_decay_M6_N2.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# gradient_method='finite_difference' through compute_optimal_rotation (pupo.py:105-127,183-184):
+# the live reference's trajectory with its own central-difference gradient (step 1e-8).
+# ------------------------------------------------------------------------------------------------
+def main_fd():
+    Pupo, _ = ref_loader.load_reference()
+    M, N = 5, 2
+    hs, gs, Ds, Gs, U0 = build_inputs(M, N, "abab", 1)
+    solver = ref_loader.make_solver(True, None)
+    calls = []
+    opt = Pupo(initial_BBstepsize=0.05, stopping_tolerance=1e-7, maxiter=12,
+               gradient_method='finite_difference', callback=lambda it, e: calls.append((it, e)))
+    U_fin, E_fin = opt.compute_optimal_rotation(
+        fun=solver.compute_rotated_energy, initial_partial_unitary=U0.clone(), oneRDM=Ds[0],
+        twoRDM=Gs[0], one_body_integrals=hs, two_body_integrals=gs)
+    obj = partial(solver.compute_rotated_energy, oneRDM=Ds[0], twoRDM=Gs[0],
+                  one_body_integrals=hs, two_body_integrals=gs)
+    fd_grad = Pupo(0.05, 1e-7, 12).compute_rotated_energy_gradient(U0.clone(), obj)
+    print(f"fd_M5_N2: {len(calls)} callbacks, E = {float(E_fin):.12f}")
+    np.savez_compressed(
+        os.path.join(HERE, "fd_M5_N2.npz"), M=M, N=N, pattern="abab", n_states=1,
+        weights=np.array([1.0]), h_spin=hs.numpy(), g_spin=gs.numpy(), D_spin_0=Ds[0].numpy(),
+        G_spin_0=Gs[0].numpy(), U0=U0.numpy(), bb0=0.05, tol=1e-7, maxiter=12,
+        opt_U=U_fin.numpy(), opt_E=float(E_fin), opt_stepsize=float(opt.BBstepsize),
+        opt_calls_it=np.array([c[0] for c in calls], dtype=np.int64),
+        opt_calls_E=np.array([float(c[1]) for c in calls], dtype=np.float64),
+        fd_grad_U0=fd_grad.numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor part of get_rotated_hamiltonian (base_opt_orb_solver.py:597-604): the two einsums exactly
+# as the reference writes them, for both spin patterns and an odd M.
+# ------------------------------------------------------------------------------------------------
+def main_rotated():
+    out = {}
+    for tag, M, N, pattern in (("a", 6, 2, "abba"), ("b", 7, 3, "abab"), ("c", 12, 4, "abba")):
+        hs, gs, _, _, U0 = build_inputs(M, N, pattern, 1, seed_shift=3)
+        W = torch.block_diag(U0, U0)
+        h_rot = torch.einsum('pq,pi,qj->ij', hs, W, W)
+        g_rot = torch.einsum('pqrs,pi,qj,rk,sl->ijkl', gs, W, W, W, W)
+        out.update({f"{tag}_M": M, f"{tag}_N": N, f"{tag}_pattern": pattern,
+                    f"{tag}_h_spin": hs.numpy(), f"{tag}_g_spin": gs.numpy(), f"{tag}_U": U0.numpy(),
+                    f"{tag}_h_rot": h_rot.numpy(), f"{tag}_g_rot": g_rot.numpy()})
+        print(f"rotated {tag}: M={M} N={N} {pattern} |g'|={float(g_rot.abs().sum()):.6f}")
+    np.savez_compressed(os.path.join(HERE, "rotated_integrals.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "fd":
+        main_fd()
+    if len(sys.argv) < 2 or sys.argv[1] == "rotated":
+        main_rotated()
     if len(sys.argv) < 2 or sys.argv[1] == "decay":
         main_decay()
     if len(sys.argv) < 2 or sys.argv[1] == "bb":
@@ -242,6 +302,8 @@ if __name__ == "__main__":
     if len(sys.argv) < 2 or sys.argv[1] == "molecule":
         main_molecule()
     if len(sys.argv) < 2 or sys.argv[1] == "inner":
-        main()
+        main(only=sys.argv[2:])
+    if len(sys.argv) >= 2 and sys.argv[1] == "big":
+        main(BIG_CASES)
     if len(sys.argv) < 2 or sys.argv[1] == "outer":
         main_outer()

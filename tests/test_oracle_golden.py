@@ -2,10 +2,10 @@
 import numpy as np
 import pytest
 
-from conftest import golden_inputs, golden_names, load_golden
+from conftest import golden_inputs, golden_inputs_spatial, golden_names, load_golden
 from oracle import oracle_np as onp
 
-SMALL = [n for n in golden_names() if "M56" not in n]
+BIG_M = 60        # above this the (2M)^4 embedding is skipped on the CPU (cfg 3: 18.7 GB)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -32,12 +32,15 @@ def test_spatial_reduction_matches_reference(name):
     from esoo_b200 import ingest
 
     gold = load_golden(name)
-    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
-    h, g, st = ingest.reduce_integrals(hs, gs)
-    D, G = ingest.reduce_rdms(Ds, Gs, st, list(gold["weights"]))
-    assert sorted(st.blocks) == sorted(
-        [(s, t, t, s) if str(gold["pattern"]) == "abba" else (s, t, s, t)
-         for s in (0, 1) for t in (0, 1)])
+    if int(gold["M"]) > BIG_M:
+        h, g, D, G, U0 = golden_inputs_spatial(gold)
+    else:
+        hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+        h, g, st = ingest.reduce_integrals(hs, gs)
+        D, G = ingest.reduce_rdms(Ds, Gs, st, list(gold["weights"]))
+        assert sorted(st.blocks) == sorted(
+            [(s, t, t, s) if str(gold["pattern"]) == "abba" else (s, t, s, t)
+             for s in (0, 1) for t in (0, 1)])
     U = U0.numpy()
     E = onp.rotated_energy_spatial(U, D.numpy(), G.numpy(), h.numpy(), g.numpy())
     grad = onp.rotated_energy_grad_spatial(U, D.numpy(), G.numpy(), h.numpy(), g.numpy())
@@ -53,25 +56,40 @@ def test_orth(name):
     assert np.max(np.abs(out - gold["orthV"])) <= 1e-12
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL if "opt_E" in load_golden(n)])
+@pytest.mark.parametrize("name", [n for n in golden_names() if "opt_E" in load_golden(n)])
 def test_optimal_rotation_trajectory(name):
-    """Driver loop, BB step and stopping rule: same callbacks, iteration count and final U."""
+    """Driver loop, BB step and stopping rule: same callbacks, iteration count and final U.
+    Measured deviations from the live reference over all fixtures (up to 445 BB steps): callback
+    energies <= 1.9e-12 relative, final U <= 4.9e-11, final energy <= 2.2e-14; the bounds below
+    are 10x those."""
     gold = load_golden(name)
-    hs, gs, Ds, Gs, U0 = golden_inputs(gold)
     from esoo_b200 import ingest
-    h, g, st = ingest.reduce_integrals(hs, gs)
-    D, G = ingest.reduce_rdms(Ds, Gs, st, list(gold["weights"]))
+    big = int(gold["M"]) > BIG_M
+    if big:
+        h, g, D, G, U0 = golden_inputs_spatial(gold)
+    else:
+        hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+        h, g, st = ingest.reduce_integrals(hs, gs)
+        D, G = ingest.reduce_rdms(Ds, Gs, st, list(gold["weights"]))
     hn, gn, Dn, Gn = h.numpy(), g.numpy(), D.numpy(), G.numpy()
+    # cfg 3 at its true size: one oracle gradient takes seconds, so only the three hand-unrolled
+    # iterations are replayed (the trajectory prefix does not depend on maxiter)
+    maxiter = 2 if big else int(gold["opt_maxiter"])
     res = onp.optimal_rotation(
         lambda U: onp.rotated_energy_spatial(U, Dn, Gn, hn, gn),
         lambda U: onp.rotated_energy_grad_spatial(U, Dn, Gn, hn, gn),
-        U0.numpy(), float(gold["opt_bb0"]), float(gold["opt_tol"]), int(gold["opt_maxiter"]))
+        U0.numpy(), float(gold["opt_bb0"]), float(gold["opt_tol"]), maxiter)
     its = [c[0] for c in res["callbacks"]]
-    assert its == list(gold["opt_calls_it"])
-    assert abs(res["energy"] - float(gold["opt_E"])) <= 1e-8
     Es = np.array([c[1] for c in res["callbacks"]])
-    assert np.max(np.abs(Es - gold["opt_calls_E"])) <= 1e-7
-    assert np.max(np.abs(res["U"] - gold["opt_U"])) <= 1e-5
+    scale = max(1.0, float(np.max(np.abs(gold["opt_calls_E"]))))
+    if big:
+        assert its == list(gold["opt_calls_it"][:len(its)]) and len(its) == 3
+        assert np.max(np.abs(Es - gold["opt_calls_E"][:3])) <= 1e-10 * scale
+        return
+    assert its == list(gold["opt_calls_it"])
+    assert abs(res["energy"] - float(gold["opt_E"])) <= 1e-12 * scale
+    assert np.max(np.abs(Es - gold["opt_calls_E"])) <= 2e-11 * scale
+    assert np.max(np.abs(res["U"] - gold["opt_U"])) <= 5e-10
 
 
 # ---------------------------------------------------------------------------------------------
@@ -170,6 +188,79 @@ def test_oracle_outer_loop_on_molecule(name):
     assert np.max(np.abs(E - gold["energies"])) <= 1e-8
     if "ref_test_golden" in gold:
         assert np.max(np.abs(E[-1] - gold["ref_test_golden"])) < 2e-5
+
+
+def test_finite_difference_trajectory_vs_reference_golden():
+    """gradient_method='finite_difference' (pupo.py:105-127, 183-184): the oracle's driver with a
+    central-difference gradient (step 1e-8) follows the live reference's FD run.  FD gradients
+    carry ~1e-8 relative noise that depends on summation order, so the trajectories agree to
+    ~1e-6, not to machine precision."""
+    gold = load_golden("fd_M5_N2")
+    D, G, h, g = gold["D_spin_0"], gold["G_spin_0"], gold["h_spin"], gold["g_spin"]
+    energy = lambda U: onp.rotated_energy_spin(U, D, G, h, g)
+
+    def fd(U):
+        out = np.empty_like(U)
+        for i in range(U.shape[0]):
+            for j in range(U.shape[1]):
+                up, um = U.copy(), U.copy()
+                up[i, j] += 1e-8
+                um[i, j] -= 1e-8
+                out[i, j] = (energy(up) - energy(um)) / 2e-8
+        return out
+
+    assert np.max(np.abs(fd(gold["U0"]) - gold["fd_grad_U0"])) <= 1e-6
+    res = onp.optimal_rotation(energy, fd, gold["U0"], float(gold["bb0"]), float(gold["tol"]),
+                               int(gold["maxiter"]))
+    assert [c[0] for c in res["callbacks"]] == list(gold["opt_calls_it"])
+    assert np.max(np.abs(np.array([c[1] for c in res["callbacks"]]) - gold["opt_calls_E"])) <= 1e-5
+    assert abs(res["energy"] - float(gold["opt_E"])) <= 1e-5
+
+
+def test_rotated_integrals_vs_reference_golden():
+    """h', g' of get_rotated_hamiltonian (base_opt_orb_solver.py:597-604), frozen from the
+    reference's own einsums: the oracle in both pictures, and the spin-block embedding
+    (esoo_b200.rotated.expand_spin_blocks) the product uses after the CUDA transform."""
+    import torch
+    from esoo_b200 import ingest, rotated
+    gold = load_golden("rotated_integrals")
+    for tag in "abc":
+        hs, gs, U = gold[f"{tag}_h_spin"], gold[f"{tag}_g_spin"], gold[f"{tag}_U"]
+        h_rot, g_rot = onp.rotated_integrals_spin(U, hs, gs)
+        assert np.max(np.abs(h_rot - gold[f"{tag}_h_rot"])) <= 1e-12
+        assert np.max(np.abs(g_rot - gold[f"{tag}_g_rot"])) <= 1e-12
+        h, g, st = ingest.reduce_integrals(torch.from_numpy(hs), torch.from_numpy(gs))
+        h_sp, g_sp = onp.rotated_integrals_spatial(U, h.numpy(), g.numpy())
+        he, ge = rotated.expand_spin_blocks(torch.from_numpy(h_sp), torch.from_numpy(g_sp), st)
+        assert np.max(np.abs(he - gold[f"{tag}_h_rot"])) <= 1e-12
+        assert np.max(np.abs(ge - gold[f"{tag}_g_rot"])) <= 1e-12
+
+
+def test_torch_port_matches_reference_golden():
+    """oracle/torch_port.py (the CPU baseline of bench.py) states the reference's einsum + autograd
+    formulation: same E and dE/dU as the live reference, in the spin-orbital and in the spatial
+    picture, and additive over slabs of the last ERI index (what the bounded sample relies on)."""
+    import torch
+    from esoo_b200 import ingest
+    from oracle import torch_port
+    for name in ("abba_M6_N2", "weighted_M6_N2_k3", "abab_M5_N2"):
+        gold = load_golden(name)
+        hs, gs, Ds, Gs, U0 = golden_inputs(gold)
+        w = list(gold["weights"])
+        _, _, E, grad = torch_port.time_reference_spin(U0, Ds, Gs, w, hs, gs)
+        assert abs(E - float(gold["E"])) <= 1e-12 * max(1.0, abs(float(gold["E"])))
+        assert np.linalg.norm(grad.numpy() - gold["grad"]) <= 1e-12 * np.linalg.norm(gold["grad"])
+        h, g, st = ingest.reduce_integrals(hs, gs)
+        D, G = ingest.reduce_rdms(Ds, Gs, st, w)
+        E2, grad2 = torch_port.energy_and_autograd(U0, D, G, h, g, 0)
+        assert abs(E2 - float(gold["E"])) <= 1e-12 * max(1.0, abs(float(gold["E"])))
+        assert np.linalg.norm(grad2.numpy() - gold["grad"]) <= 1e-12 * np.linalg.norm(gold["grad"])
+        M = h.shape[0]
+        half = M // 2
+        Ea, ga = torch_port.energy_and_autograd(U0, D, G, h, g[..., :half].contiguous(), 0)
+        Eb, gb = torch_port.energy_and_autograd(U0, D, G, h, g[..., half:].contiguous(), half)
+        assert abs(Ea + Eb - E2) <= 1e-12 * max(1.0, abs(E2))
+        assert np.linalg.norm((ga + gb - grad2).numpy()) <= 1e-12 * np.linalg.norm(gold["grad"])
 
 
 def test_bb_update_vs_reference_golden():
