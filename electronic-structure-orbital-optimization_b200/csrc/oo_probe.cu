@@ -305,7 +305,7 @@ static int cmd_time(int M, int N, int mloc, int reps, bool dense) {
   const double Npd = 8.0 * ((N + 7) / 8);
   const double flp = (double)nslab * (2.0 * M * M * Npd + 2.0 * M * Npd * Npd);
   printf("{\"cmd\": \"time\", \"mode\": \"%s\", \"slabs\": %d, \"M\": %d, \"N\": %d, \"mloc\": %d, \"reps\": %d, "
-         "\"k1_ms_avg\": %.4f, \"k1_ms_min\": %.4f, \"qc_ms\": %.4f, \"tail_ms\": %.4f, "
+         "\"k1_ms_avg\": %.4f, \"k1_ms_min\": %.4f, \"prep_ms\": %.4f, \"tail_ms\": %.4f, "
          "\"unused\": %.4f, \"eval_ms_avg\": %.4f, \"eval_ms_min\": %.4f, "
          "\"k1_gbs\": %.1f, \"k1_tflops_alg\": %.2f, \"k1_tflops_padded\": %.2f, "
          "\"evals_per_s\": %.2f}\n",

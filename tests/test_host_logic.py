@@ -58,8 +58,10 @@ def test_constructor_mirrors_reference_signature():
     # the reference's parameters in the reference's order; extensions only after them
     assert list(sig.parameters)[1:8] == ["initial_BBstepsize", "stopping_tolerance", "maxiter",
                                          "callback", "decay_factor", "gradient_method", "device"]
-    assert list(sig.parameters)[8:] == ["inputs_on_host"]
+    assert list(sig.parameters)[8:] == ["inputs_on_host", "distributed", "cache_check"]
     assert sig.parameters["inputs_on_host"].default is False
+    assert sig.parameters["distributed"].default is None
+    assert sig.parameters["cache_check"].default == "full"
     oh = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 7, device="cuda:1",
                                                      inputs_on_host=True)
     assert oh.device == "cpu" and oh.compute_device == "cuda:1"
@@ -92,7 +94,8 @@ def test_signature_matches_live_reference():
         mine = list(inspect.signature(getattr(ours, name)).parameters)
         theirs = list(inspect.signature(getattr(Ref, name)).parameters)
         if name == "__init__":                      # extensions may follow the reference's list
-            assert mine[:len(theirs)] == theirs and mine[len(theirs):] == ["inputs_on_host"]
+            assert mine[:len(theirs)] == theirs and \
+                mine[len(theirs):] == ["inputs_on_host", "distributed", "cache_check"]
         else:
             assert mine == theirs, name
 

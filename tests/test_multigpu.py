@@ -20,5 +20,5 @@ def test_two_rank_parity():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29541",
            os.path.join(ROOT, "tests", "multigpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT)
     assert "MULTIGPU PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
