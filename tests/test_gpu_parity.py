@@ -18,10 +18,11 @@ pytestmark = pytest.mark.gpu
 E_TOL = 1e-10
 G_RTOL = 1e-9
 EFINAL_TOL = 1e-8
-# whole trajectories (hundreds of BB steps) against the live reference / the oracle: bounds =
-# 10x the largest deviation measured over all fixtures (profiles/r02_parity_deviations.jsonl)
-TRAJ_E_RTOL = 1e-7
-TRAJ_U_TOL = 1e-5
+# whole trajectories (up to 445 BB steps) against the live reference / the oracle: bounds = 10x the
+# largest deviation measured on the B200 over all fixtures (profiles/r02_parity_deviations.jsonl:
+# callback energies 7.9e-12 relative, final U 5.4e-11, final energy 2.8e-14)
+TRAJ_E_RTOL = 1e-10
+TRAJ_U_TOL = 1e-9
 
 
 @pytest.fixture(scope="module")
@@ -757,7 +758,8 @@ def test_finite_difference_optimal_rotation_vs_reference_golden(torch_cuda):
     record_deviation("fd_trajectory", dE_final=abs(float(E) - float(gold["opt_E"])), dE_callbacks=dcb,
                      dU=np.max(np.abs(U.numpy() - gold["opt_U"])))
     assert [c[0] for c in calls] == list(gold["opt_calls_it"])
-    assert dcb <= 1e-5 and abs(float(E) - float(gold["opt_E"])) <= 1e-5
+    # measured on the B200: callbacks 8.1e-8, final energy 1.5e-9, final U 9.3e-9
+    assert dcb <= 1e-6 and abs(float(E) - float(gold["opt_E"])) <= 1e-7
     assert opt.last_result["n_iter"] == int(gold["opt_calls_it"][-1]) + 1
     esoo_b200.clear_engine_cache()
 
@@ -919,7 +921,8 @@ def test_spatial_integrals_through_the_class(torch_cuda):
         results.append(U.numpy())
         esoo_b200.clear_engine_cache()
     assert np.array_equal(results[0], results[1])          # packed = dense, bit for bit
-    assert np.max(np.abs(results[2] - results[0])) <= TRAJ_U_TOL
+    record_deviation("spatial_generic_vs_v4", dU=np.max(np.abs(results[2] - results[0])))
+    assert np.max(np.abs(results[2] - results[0])) <= 1e-7
 
 
 def test_generic_two_shards_sum_to_full(torch_cuda):

@@ -249,6 +249,38 @@ def _gloo_worker(rank, world, port, q):
     ok = abs(t[M * N].item() - E_ref) < 1e-12 and \
         np.max(np.abs(t[:M * N].numpy().reshape(M, N) - g_ref)) < 1e-12 and \
         FakeEngine.got == (bytes(range(128)), rank, world)
+    # ---- the host side of the sharded class path (optimizer._engine_from_spin) ----------------
+    # every rank extracts only its rows of the spatial block from the reference's spin-orbital
+    # tensor, the ranks agree on the non-zero spin blocks and on the V4 symmetry of their rows,
+    # and the pair-symmetric partial buffers (what liboo_b200 produces per GPU) sum to the total
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import shard_partial_oracle
+    from esoo_b200 import ingest
+    hs, gs = synthetic.spin_orbital_integrals(torch.from_numpy(h), torch.from_numpy(g), "abba")
+    h_sp, g_rows, st = ingest.reduce_integrals_rows_host(hs, gs, t0, mloc)
+    ok = ok and np.array_equal(g_rows.numpy(), g[rows]) and np.array_equal(h_sp.numpy(), h)
+    mask = torch.tensor([ingest.block_mask(st)], dtype=torch.int64)
+    lo, hi = mask.clone(), mask.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok = ok and int(lo) == int(hi) == ingest.block_mask(ingest.reduce_integrals(hs, gs)[2])
+    asym, gmax = ingest.v4_asymmetry_rows(gs, M, st.blocks[0], t0, mloc)
+    ok = ok and asym <= 1e-13 * gmax
+    bad = gs.clone()
+    for p_, q_, r_, s_ in ((t0, 2, 3, 1), (t0, 2 + M, 3 + M, 1), (t0 + M, 2, 3, 1 + M),
+                           (t0 + M, 2 + M, 3 + M, 1 + M)):
+        bad[p_, q_, r_, s_] += 0.5
+    ok = ok and ingest.v4_asymmetry_rows(bad, M, st.blocks[0], t0, mloc)[0] >= 0.49
+    part, e_part = shard_partial_oracle(g_rows.numpy(), t0, U, D, G, h, True)
+    t2 = torch.from_numpy(np.concatenate([part.reshape(-1), [e_part]]))
+    dist.all_reduce(t2)
+    ok = ok and abs(t2[M * N].item() - E_ref) < 1e-12 and \
+        np.max(np.abs(t2[:M * N].numpy().reshape(M, N) - g_ref)) < 1e-12
+    # pair-packed slab lists of the shards partition the full list
+    mine = distributed.pair_slab_list(M, t0, mloc)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([len(mine)]))
+    ok = ok and sum(int(c) for c in counts) == len(distributed.pair_slab_list(M))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
