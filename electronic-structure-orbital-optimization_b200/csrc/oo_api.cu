@@ -102,7 +102,7 @@ int load_nccl() {
 // ------------------------------------------------------------------------------------------------
 struct oo_ctx {
   int device = 0, M = 0, N = 0, NT = 0, Np = 0, t0 = 0, mloc = 0;
-  int num_sms = 0, nstage = 0, Mk = 0, npart = 8;
+  int num_sms = 0, nstage = 0, Mk = 0, npart = 8, box_rows = 256;
   size_t k1_smem = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -205,7 +205,9 @@ int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map, size_t nslab
   if (rc) return rc;
   const cuuint64_t dims[3] = {(cuuint64_t)c->M, (cuuint64_t)c->M, (cuuint64_t)nslab};
   const cuuint64_t strides[2] = {(cuuint64_t)c->M * 8, (cuuint64_t)c->M * c->M * 8};
-  const cuuint32_t box[3] = {K1_KC, K1_ROWS, 1};
+  // box height: the 256 rows of a pass, or just the slab's rows (rounded up to a row-block) when
+  // the whole slab is smaller -- TMA fills (and the mbarrier counts) the full box, zeros included
+  const cuuint32_t box[3] = {K1_KC, (cuuint32_t)c->box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -216,6 +218,30 @@ int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map, size_t nslab
 
 // fused = true: the evaluation path (dot products with the Q tensors in the epilogue, Aslab out);
 // fused = false: tile mode (Y / YT out), used by oo_transform only.
+// Kernel launch with the programmatic-dependent-launch attribute (see oo_common.cuh): the three
+// kernels of an evaluation and the evaluations of an optimiser chunk overlap their launch and
+// prologue with the drain of their predecessor.  Plain launch while per-kernel timing is on (the
+// events between the kernels need hard boundaries) or with OO_NO_PDL=1.
+template <typename Kernel, typename... Args>
+cudaError_t launch_chain(oo_ctx* c, Kernel kernel, dim3 grid, dim3 block, size_t smem,
+                         Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("OO_NO_PDL") != nullptr;
+  if (!off && !c->timing) {
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int NT>
 int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_tensor, bool fused) {
   K1Params p;
@@ -228,6 +254,7 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
   p.slab_coord = (pair && !c->packed) ? c->slab_coord : nullptr;   // packed: slab i is stored i-th
   p.nslab = pair ? c->nsel : c->mloc * c->M;
   p.nstage = c->nstage;
+  p.stage_tx_bytes = c->box_rows * K1_KC * (int)sizeof(double);
   p.Mk = c->Mk;
   p.upitch = c->Mk + 8;
   p.npart = c->npart;
@@ -255,9 +282,14 @@ int launch_k1_t(oo_ctx* c, const double* U, const int* done_flag, bool second_te
     attr_set[c->device & 7] = true;
   }
   const int grid = std::min(c->num_sms, p.nslab);
-  k1_half_transform<NT><<<grid, K1_THREADS, c->k1_smem, c->stream>>>(
-      second_tensor ? c->tmap2 : c->tmap, p);
-  CU_TRY(cudaGetLastError());
+  if (fused) {
+    CU_TRY(launch_chain(c, k1_half_transform<NT>, dim3(grid), dim3(K1_THREADS), c->k1_smem,
+                        second_tensor ? c->tmap2 : c->tmap, p));
+  } else {
+    k1_half_transform<NT><<<grid, K1_THREADS, c->k1_smem, c->stream>>>(
+        second_tensor ? c->tmap2 : c->tmap, p);
+    CU_TRY(cudaGetLastError());
+  }
   c->launches++;
   return OO_OK;
 }
@@ -292,12 +324,14 @@ int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, i
   pp.t0 = c->t0;
   pp.mloc = c->mloc;
   const int nbx = (Np3 + 255) / 256;
+  // rows of U per CTA: enough CTAs to fill the GPU twice, at most PREP_MAX_ROWS (shared-memory
+  // copy of the rows), as many as possible otherwise (every CTA re-reads its coefficients)
   int chunks = std::max(1, std::min(c->M, (2 * c->num_sms + nbx - 1) / nbx));
+  chunks = std::max(chunks, (c->M + PREP_MAX_ROWS - 1) / PREP_MAX_ROWS);
   chunks = std::max(chunks, (c->mloc + nbx - 1) / nbx);     // z = 2 needs nbx * chunks >= mloc CTAs
   chunks = std::min(chunks, 65535);
   pp.rows_per_chunk = (c->M + chunks - 1) / chunks;
-  k_prepare_q<NT><<<dim3(nbx, chunks, 3), 256, 0, c->stream>>>(pp);
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_chain(c, k_prepare_q<NT>, dim3(nbx, chunks, 3), dim3(256), 0, pp));
   c->launches++;
   return OO_OK;
 }
@@ -388,8 +422,7 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.accumulate = pass > 0 ? 1 : 0;
   tp.do_step = step != nullptr ? 1 : 0;
   if (step) tp.step = *step;
-  k_tail_reduce<NT><<<tp.nrows, TAIL_THREADS, 0, c->stream>>>(tp);
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_chain(c, k_tail_reduce<NT>, dim3(tp.nrows), dim3(TAIL_THREADS), 0, tp));
   c->launches++;
   return OO_OK;
 }
@@ -608,6 +641,7 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
     c->force_jacobi = (fj && *fj && *fj != '0') ? 1 : 0;
   }
   c->Mk = (M + K1_KC - 1) / K1_KC * K1_KC;
+  c->box_rows = M >= K1_ROWS ? K1_ROWS : (M + 7) / 8 * 8;
   // deepest TMA ring that fits 227 KiB; folding the 8 per-warp partial tiles into 4 or 2
   // buffers is used only when it buys another stage
   c->nstage = 0;

@@ -106,6 +106,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor in the stream is still running:
+// pdl_launch_dependents() (executed by every CTA of the predecessor, as early as possible) lets
+// the successor's CTAs be scheduled as SMs drain; pdl_wait() in the successor blocks until the
+// predecessor grid has completed and its memory is visible.  Everything a kernel reads from its
+// predecessor -- including the optimiser's stop flag -- must come after pdl_wait().  Both are
+// no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Nanosecond wall clock of the device (independent of the SM clock).
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;

@@ -57,6 +57,7 @@ struct K1Params {
                          // (pair-symmetric mode: only one of (t,q)/(q,t) is streamed); NULL = i
   int nslab;             // number of (t,q) slabs this GPU streams (dense: Mloc * M)
   int nstage;            // TMA ring depth
+  int stage_tx_bytes;    // bytes one TMA box delivers (box rows x 16 columns; <= K1_STAGE_BYTES)
   int Mk;                // M rounded up to a multiple of K1_KC
   int upitch;            // row pitch (doubles) of the transposed U copy in smem: Mk + 8
   int l2_hints;          // bit 0: stream g with the L2 evict-first policy (it is read exactly once);
@@ -196,6 +197,66 @@ __device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&ya
   k1_second_gemm_n<NT, NACT>(yacc, acc, ub2, s.u_nt_stride);
 }
 
+// <tile, Q[a]> for a = 0 .. Np-1: the epilogue's dot products of one finished N x N tile (held as
+// NCH 16-byte chunks per lane) with one Q matrix [Np][Np*Np] in L2.  The loads are issued in
+// groups of 8 (8 values of a for one chunk) and software-pipelined DEPTH groups deep, so that
+// 16-24 L2 requests are in flight per lane: with one group at a time the epilogue warps needed
+// ~1 us of L2 latency per group, more than a slab takes at N = 24, and stalled the consumers.
+// Returns the dot product for a = lane (lanes >= Np: 0); fixed shuffle tree => deterministic.
+template <int NT>
+__device__ __forceinline__ double k1_epilogue_dots(const double2 (&tile)[NT * NT], const double* Q,
+                                                   int lane, uint64_t keep) {
+  constexpr int Np = NT * 8, Np2 = Np * Np, NCH = Np2 / 64, NAG = Np / 8;
+  constexpr int DEPTH = NT <= 2 ? 3 : 2;
+  static_assert(NCH == NT * NT, "chunks per lane");
+  double mine = 0.0;
+  // group (ag, i): a = 8*ag .. 8*ag+7, chunk i.  NT <= 3: one flat, fully unrolled sequence of
+  // NAG*NCH groups; NT = 4 (64 groups): the a-group loop stays a run-time loop (code size)
+  constexpr int OUTER = NT <= 3 ? 1 : NAG;            // run-time iterations
+  constexpr int INNER = NT <= 3 ? NAG * NCH : NCH;    // unrolled groups per iteration
+#pragma unroll 1
+  for (int o = 0; o < OUTER; ++o) {
+    const double* Qo = Q + (size_t)o * 8 * Np2;       // NT = 4: this iteration's 8 rows of Q
+    double2 qv[DEPTH][8];
+    double acc[8];
+#pragma unroll
+    for (int g = 0; g < DEPTH - 1 && g < INNER; ++g) {
+      const int ag = NT <= 3 ? g / NCH : 0, i = g % NCH;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        qv[g % DEPTH][a] = ldg128_hint(Qo + (size_t)(ag * 8 + a) * Np2 + 64 * i, keep);
+    }
+#pragma unroll
+    for (int g = 0; g < INNER; ++g) {
+      if (g + DEPTH - 1 < INNER) {
+        const int gn = g + DEPTH - 1;
+        const int ag = NT <= 3 ? gn / NCH : 0, i = gn % NCH;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          qv[gn % DEPTH][a] = ldg128_hint(Qo + (size_t)(ag * 8 + a) * Np2 + 64 * i, keep);
+      }
+      const int ag = NT <= 3 ? g / NCH : o, i = g % NCH;
+      if (i == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) acc[a] = 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        acc[a] = fma(tile[i].x, qv[g % DEPTH][a].x, fma(tile[i].y, qv[g % DEPTH][a].y, acc[a]));
+      if (i == NCH - 1) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          double v = acc[a];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          if (lane == ag * 8 + a) mine = v;
+        }
+      }
+    }
+  }
+  return mine;
+}
+
 // 11 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
 // 65536 / 384 = 168 per thread (ptxas -v: NT = 1: 89, NT = 2: 125, NT = 3: 168 without spills,
 // NT = 4: 168 with ~0.9 KB of spills -- it still reaches 29 TFLOP/s).
@@ -203,7 +264,7 @@ template <int NT>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   constexpr int Np = NT * 8;
-  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  pdl_launch_dependents();
 
   extern __shared__ uint8_t k1_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -225,6 +286,10 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
   }
+  // everything above overlaps the tail of the previous kernel (programmatic dependent launch);
+  // U, the Q tensors and the stop flag are its outputs
+  pdl_wait();
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
   // Transposed, zero-padded copy of U: Ut[l][s] = U[s][l].
   for (int idx = tid; idx < Np * p.upitch; idx += K1_THREADS) {
     const int l = idx / p.upitch, s = idx - l * p.upitch;
@@ -256,7 +321,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
         for (int pass = 0; pass < npass; ++pass) {
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(empty_base + 8u * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(full_base + 8u * stage, K1_STAGE_BYTES);
+            mbar_arrive_expect_tx(full_base + 8u * stage, (uint32_t)p.stage_tx_bytes);
             if (p.l2_hints & 1)
               tma_load_3d_hint(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
                                pass * K1_ROWS, coord, full_base + 8u * stage, pol);
@@ -306,31 +371,9 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
         named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
         if (!active) continue;
         const int tl = tq / p.M, q = tq - tl * p.M;
-        const double* Q = second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np;
-        double acc[Np];
-#pragma unroll
-        for (int a = 0; a < Np; ++a) acc[a] = 0.0;
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-          for (int a0 = 0; a0 < Np; a0 += 8) {
-            double2 qv[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-              qv[a] = ldg128_hint(Q + (size_t)(a0 + a) * Np * Np + 64 * i + 2 * lane, keep);
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-              acc[a0 + a] = fma(tile[i].x, qv[a].x, fma(tile[i].y, qv[a].y, acc[a0 + a]));
-          }
-        }
-        double mine = 0.0;
-#pragma unroll
-        for (int a = 0; a < Np; ++a) {
-          double v = acc[a];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == a) mine = v;
-        }
+        const double* Q = (second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np) +
+                          2 * lane;
+        const double mine = k1_epilogue_dots<NT>(tile, Q, lane, keep);
         if (lane < Np) p.Aslab[((size_t)slab * 2 + (second ? 1 : 0)) * Np + lane] = mine;
       }
       return;

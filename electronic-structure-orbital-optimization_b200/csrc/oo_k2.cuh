@@ -244,9 +244,13 @@ struct PrepParams {
   int rows_per_chunk;
 };
 
+constexpr int PREP_MAX_ROWS = 16;   // rows of U per CTA of k_prepare_q
+
 template <int NT>
 __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
   constexpr int Np = NT * 8, Np2 = Np * Np, Np3 = Np2 * Np;
+  pdl_launch_dependents();
+  pdl_wait();                       // U (and the stop flag) come from the previous kernel
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   const int tid = threadIdx.x, N = p.N, M = p.M;
   if (blockIdx.z == 2) {
@@ -291,23 +295,35 @@ __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
   }
   const bool second = blockIdx.z == 1;
   if (second && p.G2B == nullptr) return;
+  const int nrows = second ? p.mloc : M;
+  const int r0 = blockIdx.y * p.rows_per_chunk, r1 = min(nrows, r0 + p.rows_per_chunk);
+  if (r0 >= r1) return;
+  // the chunk's rows of U, zero-padded to Np columns: read back as 16-byte broadcasts (global
+  // broadcast loads made the kernel LSU-bound: N load instructions per row and thread)
+  __shared__ double2 s_u[PREP_MAX_ROWS][Np / 2];
+  const double* Urow = p.U + (size_t)((second ? p.t0 : 0) + r0) * N;
+  for (int i = tid; i < (r1 - r0) * Np; i += 256) {
+    const int r = i / Np, c = i - r * Np;
+    reinterpret_cast<double*>(&s_u[r][0])[c] = c < N ? __ldg(Urow + (size_t)r * N + c) : 0.0;
+  }
   const int idx = blockIdx.x * 256 + tid;             // (a, e) position
-  if (idx >= Np3) return;
+  const bool valid = idx < Np3;
   const double* G2 = second ? p.G2B : p.G2A;
   double coef[Np];
 #pragma unroll
-  for (int c = 0; c < Np; ++c) coef[c] = __ldg(G2 + (size_t)c * Np3 + idx);
-  const int nrows = second ? p.mloc : M;
-  const int r0 = blockIdx.y * p.rows_per_chunk, r1 = min(nrows, r0 + p.rows_per_chunk);
-  double* out = (second ? p.QB : p.QA) + idx;
-  const double* Urow = p.U + (size_t)(second ? p.t0 : 0) * N;
-  for (int r = r0; r < r1; ++r) {
-    const double* u = Urow + (size_t)r * N;
-    double s = 0.0;
+  for (int c = 0; c < Np; ++c) coef[c] = valid ? __ldg(G2 + (size_t)c * Np3 + idx) : 0.0;
+  __syncthreads();
+  if (!valid) return;
+  double* out = (second ? p.QB : p.QA) + (size_t)r0 * Np3 + idx;
+  for (int r = 0; r < r1 - r0; ++r) {
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int c = 0; c < Np; ++c)
-      if (c < N) s = fma(__ldg(u + c), coef[c], s);
-    out[(size_t)r * Np3] = s;
+    for (int c2 = 0; c2 < Np / 2; ++c2) {
+      const double2 u = s_u[r][c2];
+      s0 = fma(u.x, coef[2 * c2], s0);
+      s1 = fma(u.y, coef[2 * c2 + 1], s1);
+    }
+    out[(size_t)r * Np3] = s0 + s1;
   }
 }
 
@@ -345,6 +361,8 @@ struct TailReduceParams {
 template <int NT>
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReduceParams p) {
   constexpr int Np = NT * 8, G = TAIL_THREADS / Np;
+  pdl_launch_dependents();
+  pdl_wait();                       // Aslab comes from K1
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   __shared__ double s_part[G][Np];
   __shared__ double s_e[Np];

@@ -134,9 +134,19 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
     scratch[tid] = s;
   }
   __syncthreads();
-  double c = 0.0;
-  for (int i = 0; i < n; ++i) c = fmax(c, scratch[i]);
+  double c = 0.0, dev = 0.0;
+  for (int i = 0; i < n; ++i) {
+    c = fmax(c, scratch[i]);
+    // |A - I| row sum: scratch holds sum_j |A_ij|; with A_ii > 0 the deviation is that sum minus
+    // A_ii plus |A_ii - 1|
+    dev = fmax(dev, scratch[i] - A[i * LD + i] + fabs(A[i * LD + i] - 1.0));
+  }
   __syncthreads();
+  // Inside the optimiser V = U - alpha G with U orthonormal, so A = V^T V is close to the identity:
+  // when ||A - I||_inf < 1/2 the iteration converges quadratically from the unscaled matrix
+  // (3-4 steps instead of 7-9 after the division by the row-sum bound, which pushes the spectrum
+  // away from 1).  The general case keeps the safe scaling.
+  if (dev < 0.5) c = 1.0;
   const double inv_c = 1.0 / c;
   for (int idx = tid; idx < nn; idx += nth) {
     const int i = idx / n, j = idx - i * n;
@@ -198,13 +208,16 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
 // U_out = orth(V) = V (V^T V)^(-1/2) for an M x N matrix V in global memory.  One CTA.  V and
 // U_out must be distinct buffers.  smem: sA, sB1, sB2, sB3 are K3_NMAX*(K3_NMAX+1) doubles each; cs 4*K3_NMAX;
 // scratch 32 doubles.
+// V is given as Va - alpha * Vb (Vb may be NULL: V = Va), so that the optimiser step needs no
+// intermediate copy of V in global memory (one dependent round trip less).
 template <int THREADS>
-__device__ inline void retract_cta(const double* V, double* Uout, int M, int N, double* sA,
-                                   double* sB1, double* sB2, double* sB3, double* cs,
-                                   double* scratch, int* sflag, int* telemetry = nullptr,
-                                   bool force_jacobi = false) {
+__device__ inline void retract_cta(const double* Va, const double* Vb, double alpha, double* Uout,
+                                   int M, int N, double* sA, double* sB1, double* sB2,
+                                   double* sB3, double* cs, double* scratch, int* sflag,
+                                   int* telemetry = nullptr, bool force_jacobi = false) {
   constexpr int LD = K3_NMAX + 1;
   const int tid = threadIdx.x, nth = blockDim.x;
+  auto V = [&](size_t idx) { return Vb ? fma(-alpha, Vb[idx], Va[idx]) : Va[idx]; };
   // Gram matrix V^T V: the t-range is split over nth / N^2 thread groups, partials summed in
   // fixed order through shared memory (sB3 is free until the Newton-Schulz iteration starts)
   {
@@ -219,10 +232,10 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
       int t = tb;
 #pragma unroll 4
       for (; t + 1 < te; t += 2) {
-        s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
-        s1 = fma(V[(size_t)(t + 1) * N + i], V[(size_t)(t + 1) * N + j], s1);
+        s0 = fma(V((size_t)t * N + i), V((size_t)t * N + j), s0);
+        s1 = fma(V((size_t)(t + 1) * N + i), V((size_t)(t + 1) * N + j), s1);
       }
-      if (t < te) s0 = fma(V[(size_t)t * N + i], V[(size_t)t * N + j], s0);
+      if (t < te) s0 = fma(V((size_t)t * N + i), V((size_t)t * N + j), s0);
       sB3[part * nn + e] = s0 + s1;
     }
     __syncthreads();
@@ -268,13 +281,13 @@ __device__ inline void retract_cta(const double* V, double* Uout, int M, int N, 
     scale = 1.0;
     __syncthreads();
   }
-  // U = V S  (V and Uout must not alias): nth / M threads share a row, each a subset of columns
+  // U = V S  (Va, Vb and Uout must not alias): nth / M threads share a row, each a subset of columns
   {
     const int per_row = max(1, nth / M);
     for (int idx = tid; idx < M * per_row; idx += nth) {
       const int t = idx / per_row, grp = idx - t * per_row;
       double v[K3_NMAX];
-      for (int j = 0; j < N; ++j) v[j] = V[(size_t)t * N + j] * scale;
+      for (int j = 0; j < N; ++j) v[j] = V((size_t)t * N + j) * scale;
       for (int j = grp; j < N; j += per_row) {
         double s = 0.0;
         for (int m = 0; m < N; ++m) s = fma(v[m], S[m * LD + j], s);
@@ -290,8 +303,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_orth(const double* V, double* Uo
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
       sB2[K3_NMAX * (K3_NMAX + 1)], sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
   __shared__ int sflag;
-  retract_cta<K3_THREADS>(V, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
-                          force_jacobi != 0);
+  retract_cta<K3_THREADS>(V, nullptr, 0.0, Uout, M, N, sA, sB1, sB2, sB3, cs, scratch, &sflag,
+                          nullptr, force_jacobi != 0);
 }
 
 struct StepParams {
@@ -310,9 +323,48 @@ struct StepParams {
 // Shared memory of one optimiser transition / retraction.
 struct StepSmem {
   double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)], sB2[K3_NMAX * (K3_NMAX + 1)],
-      sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33];
+      sB3[K3_NMAX * (K3_NMAX + 1)], cs[4 * K3_NMAX], scratch[33], scratch3[3 * 33];
   int sflag;
 };
+
+// Three deterministic block-wide sums at once (fixed shuffle trees): one pair of barriers instead
+// of three.  scratch3: 99 doubles.  Results valid in every thread.
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* scratch3) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+    scratch3[warp] = a;
+    scratch3[33 + warp] = b;
+    scratch3[66 + warp] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double ta = lane < nw ? scratch3[lane] : 0.0, tb = lane < nw ? scratch3[33 + lane] : 0.0,
+           tc = lane < nw ? scratch3[66 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ta += __shfl_xor_sync(0xffffffffu, ta, o);
+      tb += __shfl_xor_sync(0xffffffffu, tb, o);
+      tc += __shfl_xor_sync(0xffffffffu, tc, o);
+    }
+    if (lane == 0) {
+      scratch3[32] = ta;
+      scratch3[65] = tb;
+      scratch3[98] = tc;
+    }
+  }
+  __syncthreads();
+  a = scratch3[32];
+  b = scratch3[65];
+  c = scratch3[98];
+}
 
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
 // Called by every thread of ONE CTA of THREADS threads (the stand-alone k_step kernel, or the last
@@ -372,21 +424,17 @@ __device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
       ug = fma(du, dg, ug);
       gg = fma(dg, dg, gg);
     }
-    uu = block_sum(uu, sm.scratch);
-    ug = block_sum(ug, sm.scratch);
-    gg = block_sum(gg, sm.scratch);
+    block_sum3(uu, ug, gg, sm.scratch3);
     alpha = (k & 1) ? uu / fabs(ug) : fabs(ug) / gg;
   }
-  // ---- V = U_k - alpha G_k; shift histories ---------------------------------
+  // ---- shift histories; V = U_k - alpha G_k is formed on the fly from the shifted copies ------
   for (int i = tid; i < MN; i += nth) {
-    const double u = p.Ucur[i], g = p.gE[i];
-    p.Vtmp[i] = u - alpha * g;
-    p.Uprev[i] = u;
-    p.Gprev[i] = g;
+    p.Uprev[i] = p.Ucur[i];
+    p.Gprev[i] = p.gE[i];
   }
   __syncthreads();
-  retract_cta<THREADS>(p.Vtmp, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3, sm.cs, sm.scratch,
-                       &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
+  retract_cta<THREADS>(p.Uprev, p.Gprev, alpha, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3,
+                       sm.cs, sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
@@ -436,10 +484,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
     gg = block_sum(gg, scratch);
     alpha = (p.iteration & 1) ? uu / fabs(ug) : fabs(ug) / gg;
   }
-  for (int i = tid; i < MN; i += nth) p.Vtmp[i] = p.Ucur[i] - alpha * p.Gcur[i];
-  __syncthreads();
-  retract_cta<K3_THREADS>(p.Vtmp, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch, &sflag, nullptr,
-                          p.force_jacobi != 0);
+  retract_cta<K3_THREADS>(p.Ucur, p.Gcur, alpha, p.Unew, p.M, p.N, sA, sB1, sB2, sB3, cs, scratch,
+                          &sflag, nullptr, p.force_jacobi != 0);
   if (tid == 0) *p.alpha_io = alpha;
 }
 
