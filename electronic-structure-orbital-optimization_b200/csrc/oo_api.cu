@@ -115,6 +115,8 @@ struct oo_ctx {
   double* G2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // k_prepare_gamma2 kinds
   double *QA = nullptr, *QB = nullptr, *Aslab = nullptr;   // fused evaluation (oo_k1.cuh)
   bool step_fusable = true;            // OO_NO_STEP_FUSION=1: k_step stays a separate launch
+  bool tiles_eval = false;             // evaluation through stored tiles (N in 25..32; OO_EVAL_PATH)
+  double* Gp = nullptr;                // tiles path: 2-RDM, V4-averaged, [Np^3][Np]
   unsigned gflags = 0;
   bool have_ints = false, have_rdms = false;
   alignas(64) CUtensorMap tmap;
@@ -218,6 +220,21 @@ int build_tmap(oo_ctx* c, const double* base, CUtensorMap* out_map, size_t nslab
 
 // fused = true: the evaluation path (dot products with the Q tensors in the epilogue, Aslab out);
 // fused = false: tile mode (Y / YT out), used by oo_transform only.
+void fill_peer_comm(oo_ctx* c, PeerComm& cm) {
+  cm.enabled = 1;
+  cm.rank = c->rank;
+  cm.world = c->world;
+  cm.stride = c->peer_stride;
+  cm.seq_ptr = c->peer_seq_dev;
+  cm.error_flag = c->peer_err;
+  cm.error_flag_host = c->peer_err_host_dev;
+  cm.timeout_ns = c->peer_timeout_ns;
+  for (int r = 0; r < c->world; ++r) {
+    cm.flags[r] = (unsigned long long*)c->peer_map[r];
+    cm.slots[r] = (double*)((char*)c->peer_map[r] + 256);
+  }
+}
+
 // Kernel launch with the programmatic-dependent-launch attribute (see oo_common.cuh): the three
 // kernels of an evaluation and the evaluations of an optimiser chunk overlap their launch and
 // prologue with the drain of their predecessor.  Plain launch while per-kernel timing is on (the
@@ -306,7 +323,8 @@ int launch_k1(oo_ctx* c, const double* U, const int* done_flag, bool second_tens
 
 // Q tensors (QA for every orbital, QB for the shard's rows) and the one-body rows.
 template <int NT>
-int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB) {
+int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB,
+                  bool onebody_only) {
   constexpr int Np3 = NT * 8 * NT * 8 * NT * 8;
   PrepParams pp;
   pp.U = U;
@@ -323,6 +341,7 @@ int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, i
   pp.N = c->N;
   pp.t0 = c->t0;
   pp.mloc = c->mloc;
+  pp.onebody_only = onebody_only ? 1 : 0;
   const int nbx = (Np3 + 255) / 256;
   // rows of U per CTA: enough CTAs to fill the GPU twice, at most PREP_MAX_ROWS (shared-memory
   // copy of the rows), as many as possible otherwise (every CTA re-reads its coefficients)
@@ -336,12 +355,13 @@ int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, i
   return OO_OK;
 }
 
-int launch_prep(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB) {
+int launch_prep(oo_ctx* c, const double* U, const int* done_flag, int kindA, int kindB,
+                bool onebody_only = false) {
   switch (c->NT) {
-    case 1: return launch_prep_t<1>(c, U, done_flag, kindA, kindB);
-    case 2: return launch_prep_t<2>(c, U, done_flag, kindA, kindB);
-    case 3: return launch_prep_t<3>(c, U, done_flag, kindA, kindB);
-    case 4: return launch_prep_t<4>(c, U, done_flag, kindA, kindB);
+    case 1: return launch_prep_t<1>(c, U, done_flag, kindA, kindB, onebody_only);
+    case 2: return launch_prep_t<2>(c, U, done_flag, kindA, kindB, onebody_only);
+    case 3: return launch_prep_t<3>(c, U, done_flag, kindA, kindB, onebody_only);
+    case 4: return launch_prep_t<4>(c, U, done_flag, kindA, kindB, onebody_only);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -385,20 +405,7 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
                   int pass, const StepParams* step) {
   TailReduceParams tp;
   memset(&tp, 0, sizeof tp);
-  if (fused) {
-    tp.comm.enabled = 1;
-    tp.comm.rank = c->rank;
-    tp.comm.world = c->world;
-    tp.comm.stride = c->peer_stride;
-    tp.comm.seq_ptr = c->peer_seq_dev;
-    tp.comm.error_flag = c->peer_err;
-    tp.comm.error_flag_host = c->peer_err_host_dev;
-    tp.comm.timeout_ns = c->peer_timeout_ns;
-    for (int r = 0; r < c->world; ++r) {
-      tp.comm.flags[r] = (unsigned long long*)c->peer_map[r];
-      tp.comm.slots[r] = (double*)((char*)c->peer_map[r] + 256);
-    }
-  }
+  if (fused) fill_peer_comm(c, tp.comm);
   const bool pair = c->pair_sym && !c->generic;
   tp.Aslab = c->Aslab;
   tp.rowstart = pair ? c->rowstart : nullptr;
@@ -434,6 +441,50 @@ int launch_tail(oo_ctx* c, const double* U, double* out, const int* done_flag, b
     case 2: return launch_tail_t<2>(c, U, out, done_flag, fused, pass, step);
     case 3: return launch_tail_t<3>(c, U, out, done_flag, fused, pass, step);
     case 4: return launch_tail_t<4>(c, U, out, done_flag, fused, pass, step);
+  }
+  return fail(OO_ERR_INVALID, "unsupported N");
+}
+
+// Tiles path: 2-RDM contraction of T3 (k_tail_row), energy, all-reduce, optional optimiser step.
+template <int NT>
+int launch_tail_row_t(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
+                      const StepParams* step) {
+  TailParams tp;
+  memset(&tp, 0, sizeof tp);
+  if (fused) fill_peer_comm(c, tp.comm);
+  tp.T3 = c->T3;
+  tp.Gp = c->Gp;
+  tp.U = U;
+  tp.B1 = c->B1;
+  tp.B12 = c->B12;
+  tp.out = out;
+  tp.rowE = c->rowE;
+  tp.counter = c->counter;
+  tp.done_flag = done_flag;
+  tp.M = c->M;
+  tp.N = c->N;
+  tp.t0 = c->t0;
+  tp.mloc = c->mloc;
+  tp.row0 = c->pair_sym ? 0 : c->t0;
+  tp.nrows = c->pair_sym ? c->M : c->mloc;
+  tp.two_body_grad_factor = 4.0;
+  tp.accumulate = 0;
+  tp.do_step = step != nullptr ? 1 : 0;
+  if (step) tp.step = *step;
+  constexpr int R = tail_rows(NT), AC = tail_ac(NT);
+  dim3 grid((tp.nrows + R - 1) / R, (NT * 8) / AC);
+  CU_TRY(launch_chain(c, k_tail_row<NT>, grid, dim3(TAIL_THREADS), 0, tp));
+  c->launches++;
+  return OO_OK;
+}
+
+int launch_tail_row(oo_ctx* c, const double* U, double* out, const int* done_flag, bool fused,
+                    const StepParams* step) {
+  switch (c->NT) {
+    case 1: return launch_tail_row_t<1>(c, U, out, done_flag, fused, step);
+    case 2: return launch_tail_row_t<2>(c, U, out, done_flag, fused, step);
+    case 3: return launch_tail_row_t<3>(c, U, out, done_flag, fused, step);
+    case 4: return launch_tail_row_t<4>(c, U, out, done_flag, fused, step);
   }
   return fail(OO_ERR_INVALID, "unsupported N");
 }
@@ -477,6 +528,22 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, 
     if ((rc = launch_prep(c, U, done_flag, 4, 5))) return rc;
     if ((rc = launch_k1(c, U, done_flag, true, true))) return rc;
     if ((rc = launch_tail(c, U, out, done_flag, fused, 1, step_in_tail))) return rc;
+  } else if (c->tiles_eval) {
+    // tiles path (N in 25..32): one-body rows, K1 storing the tiles, q-contraction, T3 x 2-RDM
+    if ((rc = launch_prep(c, U, done_flag, 0, -1, true))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = launch_k1(c, U, done_flag, false, false))) return rc;
+    if (tm) CU_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = launch_qc(c, done_flag))) return rc;
+    if (!pair && c->mloc < c->M) {
+      const size_t N = (size_t)c->N;
+      if (c->t0 > 0) CU_TRY(cudaMemsetAsync(out, 0, (size_t)c->t0 * N * sizeof(double), c->stream));
+      const size_t end = (size_t)(c->t0 + c->mloc);
+      if (end < (size_t)c->M)
+        CU_TRY(cudaMemsetAsync(out + end * N, 0, ((size_t)c->M - end) * N * sizeof(double),
+                               c->stream));
+    }
+    if ((rc = launch_tail_row(c, U, out, done_flag, fused, step_in_tail))) return rc;
   } else {
     if ((rc = launch_prep(c, U, done_flag, 0, pair ? 1 : -1))) return rc;
     if (tm) CU_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -546,6 +613,13 @@ int ensure_transform_ws(oo_ctx* c) {
 int prepare_gammas(oo_ctx* c, const double* G_dev) {
   int rc = ensure_eval_ws(c, c->generic);
   if (rc) return rc;
+  if (c->tiles_eval && !c->generic) {
+    if ((rc = ensure_transform_ws(c))) return rc;
+    if ((rc = alloc_zero(&c->Gp, (size_t)c->Np * c->Np * c->Np * c->Np))) return rc;
+    k_prepare_gamma<<<c->N * c->Np, 256, 0, c->stream>>>(G_dev, c->Gp, c->N, c->Np, 1);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+  }
   for (int k = c->generic ? 2 : 0; k < (c->generic ? 6 : 2); ++k) {
     k_prepare_gamma2<<<c->Np * c->Np, 256, 0, c->stream>>>(G_dev, c->G2[k], c->N, c->Np, k);
     CU_TRY(cudaGetLastError());
@@ -715,6 +789,15 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   {
     const char* nf = getenv("OO_NO_STEP_FUSION");
     c->step_fusable = !(nf && *nf && *nf != '0');
+    // N <= 24: the 2-RDM contraction is fused into K1's epilogue; N in 25..32: the epilogue's two
+    // dot-product warps would need 2048 FP64 instructions per slab and stall the consumers
+    // (measured: K1 1.33 -> 2.10 ms at M=256, N=32), so K1 stores the tiles and
+    // k_qcontract / k_tail_row finish the evaluation.  OO_EVAL_PATH=fused|tiles overrides.
+    c->tiles_eval = c->NT >= 4;
+    if (const char* ep = getenv("OO_EVAL_PATH")) {
+      if (!strcmp(ep, "tiles")) c->tiles_eval = true;
+      if (!strcmp(ep, "fused")) c->tiles_eval = false;
+    }
   }
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
@@ -742,6 +825,7 @@ int oo_destroy(oo_ctx* c) {
     if (c->peer_map[r] && c->peer_map[r] != c->peer_base) cudaIpcCloseMemHandle(c->peer_map[r]);
   for (int s2 = 0; s2 < 6; ++s2)
     if (c->G2[s2]) cudaFree(c->G2[s2]);
+  if (c->Gp) cudaFree(c->Gp);
   if (c->QA) cudaFree(c->QA);
   if (c->QB) cudaFree(c->QB);
   if (c->Aslab) cudaFree(c->Aslab);

@@ -65,6 +65,39 @@ __global__ void __launch_bounds__(256) k_v4_symmetry_tiles(const double* __restr
   }
 }
 
+// Logical Gp[a][j][l*Np+k] = (1/4)(G[a,j,k,l] + G[j,a,l,k] + G[k,l,a,j] + G[l,k,j,a])  (V4 average),
+// zero in the padding (j, k or l >= N).  grid N*Np, block Np*Np threads (looped).
+// symmetrise = 0 selects one of the four slot layouts of the generic (no symmetry) gradient:
+//   slot 0: Gp[a][j][l*Np+k] = G[a,j,k,l]      slot 1: Gp[a][i][l*Np+k] = G[i,a,k,l]
+//   slot 2: Gp[a][l][j*Np+i] = G[i,j,a,l]      slot 3: Gp[a][k][j*Np+i] = G[i,j,k,a]
+// (middle index = the plane index of T3, tile index = (row, col) of the K1 tile as stored).
+__global__ void k_prepare_gamma(const double* __restrict__ G, double* __restrict__ Gp, int N, int Np,
+                                int symmetrise, int slot = 0) {
+  const int a = blockIdx.x / Np, j = blockIdx.x % Np;
+  const int Np2 = Np * Np;
+  const size_t N2 = (size_t)N * N, N3 = N2 * N;
+  for (int e = threadIdx.x; e < Np2; e += blockDim.x) {
+    const int l = e / Np, k = e - l * Np;
+    double v = 0.0;
+    if (j < N && k < N && l < N) {
+      if (!symmetrise && slot == 1) v = G[j * N3 + a * N2 + (size_t)k * N + l];
+      else if (!symmetrise && slot == 2) v = G[k * N3 + l * N2 + (size_t)a * N + j];
+      else if (!symmetrise && slot == 3) v = G[k * N3 + l * N2 + (size_t)j * N + a];
+      else v = G[a * N3 + j * N2 + (size_t)k * N + l];
+      if (symmetrise) {
+        v += G[j * N3 + a * N2 + (size_t)l * N + k];
+        v += G[k * N3 + l * N2 + (size_t)a * N + j];
+        v += G[l * N3 + k * N2 + (size_t)j * N + a];
+        v *= 0.25;
+      }
+    }
+    // storage: a fastest, Gp[(j*Np2 + e)*Np + a] (rows a >= N stay zero from the allocation):
+    // the tail kernel reads all a of one (j,e) with unit stride; strides of Np^3 doubles between
+    // the a-planes made every CTA hit the same L2 slices at the same time (measured 10x slower)
+    Gp[((size_t)j * Np2 + e) * Np + a] = v;
+  }
+}
+
 // 2-RDM in the layout of the fused evaluation (k_prepare_q): G2[c][a][e], c = the index that is
 // contracted with U, a = the gradient column, e = e1*Np + e0 the position inside a K1 tile
 // (tile[e1*Np + e0] = Y[e0][e1], Y = U^T g_slab U).  Zero in the padding.  `kind` selects what is

@@ -16,20 +16,20 @@
 //                                                 the 8x8 C fragment of m8n8k4 is two 8x4 A
 //                                                 fragments with a permuted k order), B = U^T (smem)
 // Work decomposition: persistent CTAs (one per SM), slabs dealt round-robin; inside a CTA one TMA
-// producer warp, two epilogue warps (per-slab reduction, off the MMA critical path) and
-// 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
+// producer warp, three epilogue warps (per-slab reduction + fused 2-RDM contraction, off the MMA
+// critical path) and 8 consumer warps, every consumer warp owns up to 4 row-blocks (8 rows each) of
 // the current 256-row pass and all of its columns, so the second contraction costs a fixed N/M
 // fraction of the first.
 //
 // Fused 2-RDM contraction (energy / gradient evaluations).  The rows of A = dE2/dU / 4 are
 //      A[t][a] = sum_q <Y_tq, QA_q[a]>   +   sum_{t'} <Y_t't, QB_t'[a]>   (second sum: pair mode)
 // with QA_q[a][e] = sum_j U[q][j] Gamma~[a][j][e] (k_prepare_q; depends on U and the 2-RDM only).
-// The epilogue warps therefore never store the N x N tiles: warp A takes the dot products of the
-// finished tile with QA_q (row t of A), warp B with QB_t (row q of A: the transposed tile of the
-// pair partner, the transposition folded into QB's layout), and they write 2 x Np doubles per
-// slab (Aslab).  The tiles, the q-contraction and the T3 tensor disappear from the evaluation;
+// The epilogue warps therefore never store the N x N tiles: warp C sums the consumers' partial
+// tiles, warp A takes the dot products of the finished tile with QA_q (row t of A), warp B with
+// QB_t (row q of A: the transposed tile of the pair partner, the transposition folded into QB's
+// layout), and they write 2 x Np doubles per slab (Aslab).  The tiles, the q-contraction and the T3 tensor disappear from the evaluation;
 // what is left after K1 is a fixed-order sum of Aslab records per row (k_tail_reduce).
-// Tile mode (p.QA == NULL; oo_transform only) stores Y (warp A) and its transpose (warp B).
+// Tile mode (p.QA == NULL; oo_transform only): warp C stores Y and its transpose.
 #pragma once
 #include "oo_common.cuh"
 
@@ -40,11 +40,11 @@ constexpr int K1_RB = 4;                           // 8-row blocks per consumer 
 constexpr int K1_ROWS = K1_NWARP * K1_RB * 8;      // slab rows per pass = TMA box height (256)
 constexpr int K1_KC = 16;                          // slab columns per stage (128 B swizzle span)
 constexpr int K1_STAGE_BYTES = K1_ROWS * K1_KC * 8;  // 32 KiB
-constexpr int K1_THREADS = (K1_NWARP + 3) * 32;    // + 1 TMA producer warp + 2 epilogue warps
+constexpr int K1_THREADS = (K1_NWARP + 4) * 32;    // + 1 TMA producer warp + 3 epilogue warps
 constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
 constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
 constexpr int K1_BAR_FOLD = 3;                     // first of the two-warp hand-over barriers (ids 3..12)
-constexpr int K1_BAR_COUNT = (K1_NWARP + 2) * 32;  // consumers + the two epilogue warps
+constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + the summing epilogue warp
 
 struct K1Params {
   const double* U;       // [M][N] row-major partial unitary
@@ -78,7 +78,8 @@ static inline size_t k1_smem_bytes(int NT, int Mk, int nstage, int npart = K1_NW
   size_t b = (size_t)nstage * K1_STAGE_BYTES;           // TMA ring
   b += (size_t)Np * (Mk + 8) * sizeof(double);          // Ut
   b += (size_t)npart * Np * Np * sizeof(double);        // partial-tile buffers (8, 4 or 2)
-  b += (size_t)2 * nstage * sizeof(uint64_t);           // full/empty mbarriers
+  b += (size_t)2 * Np * Np * sizeof(double);            // finished tiles, double buffered
+  b += (size_t)(2 * nstage + 4) * sizeof(uint64_t);     // full/empty + tile full/free mbarriers
   return b + 1024;                                      // alignment slack
 }
 
@@ -198,22 +199,26 @@ __device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&ya
 }
 
 // <tile, Q[a]> for a = 0 .. Np-1: the epilogue's dot products of one finished N x N tile (held as
-// NCH 16-byte chunks per lane) with one Q matrix [Np][Np*Np] in L2.  The loads are issued in
-// groups of 8 (8 values of a for one chunk) and software-pipelined DEPTH groups deep, so that
-// 16-24 L2 requests are in flight per lane: with one group at a time the epilogue warps needed
-// ~1 us of L2 latency per group, more than a slab takes at N = 24, and stalled the consumers.
-// Returns the dot product for a = lane (lanes >= Np: 0); fixed shuffle tree => deterministic.
+// NCH 16-byte chunks per lane) with one Q matrix [Np][Np*Np] in L2; the Np results go to out[].
+// FP64 instructions are the scarce resource here: the two consumer warps that share the
+// sub-partition keep its FP64 pipe busy with DMMAs, and every DFMA / DADD of this warp waits for a
+// gap (ncu: stall_math on ~all of them, ~85 cycles each).  Hence
+//   * one DFMA pair per (a, chunk) and nothing else in the loop,
+//   * a transposing shuffle reduction: 8 accumulators are reduced with 4+2+1+1+1 = 9 DADDs
+//     instead of 8 x 5 (each exchange step halves the number of live values per lane),
+//   * loads in groups of 8, two groups in flight.
+// Fixed shuffle tree => deterministic.
 template <int NT>
-__device__ __forceinline__ double k1_epilogue_dots(const double2 (&tile)[NT * NT], const double* Q,
-                                                   int lane, uint64_t keep) {
+__device__ __forceinline__ void k1_epilogue_dots(const double2 (&tile)[NT * NT], const double* Q,
+                                                 int lane, uint64_t keep, double* out) {
   constexpr int Np = NT * 8, Np2 = Np * Np, NCH = Np2 / 64, NAG = Np / 8;
-  constexpr int DEPTH = NT <= 2 ? 3 : 2;
+  constexpr int DEPTH = 2;
   static_assert(NCH == NT * NT, "chunks per lane");
-  double mine = 0.0;
   // group (ag, i): a = 8*ag .. 8*ag+7, chunk i.  NT <= 3: one flat, fully unrolled sequence of
   // NAG*NCH groups; NT = 4 (64 groups): the a-group loop stays a run-time loop (code size)
   constexpr int OUTER = NT <= 3 ? 1 : NAG;            // run-time iterations
   constexpr int INNER = NT <= 3 ? NAG * NCH : NCH;    // unrolled groups per iteration
+  const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
 #pragma unroll 1
   for (int o = 0; o < OUTER; ++o) {
     const double* Qo = Q + (size_t)o * 8 * Np2;       // NT = 4: this iteration's 8 rows of Q
@@ -238,27 +243,40 @@ __device__ __forceinline__ double k1_epilogue_dots(const double2 (&tile)[NT * NT
       const int ag = NT <= 3 ? g / NCH : o, i = g % NCH;
       if (i == 0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a) acc[a] = 0.0;
+        for (int a = 0; a < 8; ++a)
+          acc[a] = fma(tile[0].x, qv[g % DEPTH][a].x, tile[0].y * qv[g % DEPTH][a].y);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          acc[a] = fma(tile[i].x, qv[g % DEPTH][a].x, fma(tile[i].y, qv[g % DEPTH][a].y, acc[a]));
       }
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        acc[a] = fma(tile[i].x, qv[g % DEPTH][a].x, fma(tile[i].y, qv[g % DEPTH][a].y, acc[a]));
       if (i == NCH - 1) {
+        // transposing reduction over the 32 lanes: after the steps 16, 8, 4 a lane holds ONE
+        // value, the partial sum for a = 4*bit4 + 2*bit3 + bit2 of its lane id; steps 2, 1 finish
+        double v4[4], v2[2], v;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          double v = acc[a];
-#pragma unroll
-          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-          if (lane == ag * 8 + a) mine = v;
+        for (int k = 0; k < 4; ++k) {
+          const double keepv = up16 ? acc[k + 4] : acc[k], send = up16 ? acc[k] : acc[k + 4];
+          v4[k] = keepv + __shfl_xor_sync(0xffffffffu, send, 16);
         }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const double keepv = up8 ? v4[k + 2] : v4[k], send = up8 ? v4[k] : v4[k + 2];
+          v2[k] = keepv + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+          const double keepv = up4 ? v2[1] : v2[0], send = up4 ? v2[0] : v2[1];
+          v = keepv + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if ((lane & 3) == 0) out[ag * 8 + (lane >> 2)] = v;
       }
     }
   }
-  return mine;
 }
 
-// 11 warps are allocated as 12 (warp allocation granularity 4), so the register cap is
-// 65536 / 384 = 168 per thread (ptxas -v: NT = 1: 89, NT = 2: 125, NT = 3: 168 without spills,
+// 12 warps: the register cap is 65536 / 384 = 168 per thread (ptxas -v: NT = 1: 89, NT = 2: 125, NT = 3: 168 without spills,
 // NT = 4: 168 with ~0.9 KB of spills -- it still reaches 29 TFLOP/s).
 template <int NT>
 __global__ void __launch_bounds__(K1_THREADS, 1)
@@ -271,17 +289,24 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       (reinterpret_cast<uintptr_t>(k1_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   double* Ut = reinterpret_cast<double*>(smem + (size_t)p.nstage * K1_STAGE_BYTES);
   double* Ypart = Ut + (size_t)Np * p.upitch;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ypart + p.npart * Np * Np);
+  double* Tbuf = Ypart + p.npart * Np * Np;              // [2][Np*Np] finished tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Tbuf + 2 * Np * Np);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t stage_base = smem_u32(smem);
   const uint32_t full_base = smem_u32(bars);
   const uint32_t empty_base = full_base + 8u * p.nstage;
+  const uint32_t tfull_base = empty_base + 8u * p.nstage;   // [2] tile buffer filled (1 arrival)
+  const uint32_t tfree_base = tfull_base + 16u;             // [2] tile buffer read (2 arrivals)
 
   if (tid == 0) {
     for (int s = 0; s < p.nstage; ++s) {
       mbar_init(full_base + 8u * s, 1);
       mbar_init(empty_base + 8u * s, K1_NWARP);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_base + 8u * b, 1);
+      mbar_init(tfree_base + 8u * b, 2);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
@@ -339,69 +364,93 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     return;
   }
 
-  if (warp > K1_NWARP) {
-    // ------------------------------ epilogue warps ------------------------------
-    // Take the per-slab reduction off the consumers' critical path: they only drop their
-    // partial tiles into shared memory and go on with the next slab.  Both warps sum the
-    // partials in fixed order (deterministic) into registers and release the buffer at once.
-    const bool second = warp == K1_NWARP + 2;
+  if (warp == K1_NWARP + 1) {
+    // ------------------------------ epilogue warp C: the summer ------------------------------
+    // Takes the per-slab reduction off the consumers' critical path: they only drop their
+    // partial tiles into shared memory and go on with the next slab.  This warp sums the
+    // partials in fixed order (deterministic), releases the partial-tile buffers at once and
+    // hands the finished tile to the two dot-product warps through a double-buffered tile
+    // (fused mode) or stores it and its transpose (tile mode).
     constexpr int NCH = Np * Np / 64;                      // 16-byte chunks of the tile per lane
-    named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);           // the buffer starts out free
-    if (p.QA != nullptr) {
-      // ---- fused mode: dot products with the Q tensors, 2 x Np doubles per slab ----
-      const uint64_t keep = l2_policy_evict_last();
-      const bool active = !second || p.QB != nullptr;
-      for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
-        const int tq = p.slab_tq ? __ldg(p.slab_tq + slab) : slab;
-        named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
-        double2 tile[NCH];
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < NCH; ++i) {
-            double2 s2 = make_double2(0.0, 0.0);
-            for (int w = 0; w < p.npart; ++w) {
-              const double2 v =
-                  *reinterpret_cast<const double2*>(Ypart + w * Np * Np + 64 * i + 2 * lane);
-              s2.x += v.x;
-              s2.y += v.y;
-            }
-            tile[i] = s2;
-          }
-        }
-        named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
-        if (!active) continue;
-        const int tl = tq / p.M, q = tq - tl * p.M;
-        const double* Q = (second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np) +
-                          2 * lane;
-        const double mine = k1_epilogue_dots<NT>(tile, Q, lane, keep);
-        if (lane < Np) p.Aslab[((size_t)slab * 2 + (second ? 1 : 0)) * Np + lane] = mine;
-      }
-      return;
-    }
-    // ---- tile mode: warp A stores the tile, warp B its transpose (pair-symmetric mode) ----
+    named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);           // the buffers start out free
     const uint64_t keep = l2_policy_evict_last();
-    for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
+    int it = 0;
+    for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x, ++it) {
       named_bar_sync(K1_BAR_FULL, K1_BAR_COUNT);
-      double* out = second ? (p.YT ? p.YT + (size_t)slab * Np * Np : nullptr)
-                           : p.Y + (size_t)slab * Np * Np;
-      double sums[Np * Np / 32];
+      double2 tile[NCH];
 #pragma unroll
-      for (int i = 0; i < Np * Np / 32; ++i) {
-        double s = 0.0;
-        for (int w = 0; w < p.npart; ++w) s += Ypart[w * Np * Np + i * 32 + lane];
-        sums[i] = s;
+      for (int i = 0; i < NCH; ++i) {
+        double2 s2 = make_double2(0.0, 0.0);
+        for (int w = 0; w < p.npart; ++w) {
+          const double2 v =
+              *reinterpret_cast<const double2*>(Ypart + w * Np * Np + 64 * i + 2 * lane);
+          s2.x += v.x;
+          s2.y += v.y;
+        }
+        tile[i] = s2;
       }
       named_bar_arrive(K1_BAR_FREE, K1_BAR_COUNT);
-      if (out == nullptr) continue;
+      if (p.QA != nullptr) {
+        const int b = it & 1, n = it >> 1;                 // n-th use of tile buffer b
+        if (n > 0) mbar_wait(tfree_base + 8u * b, (uint32_t)((n - 1) & 1));
+        double2* dst = reinterpret_cast<double2*>(Tbuf + b * Np * Np) + lane;
 #pragma unroll
-      for (int i = 0; i < Np * Np / 32; ++i) {
-        const int e = i * 32 + lane;
-        // the transposed copy lets the pair-symmetric q-contraction read both orientations
-        // with unit stride
-        double* dst = second ? out + (e % Np) * Np + e / Np : out + e;
-        if (p.l2_hints & 2) st_global_hint(dst, sums[i], keep);
-        else *dst = sums[i];
+        for (int i = 0; i < NCH; ++i) dst[32 * i] = tile[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tfull_base + 8u * b);
+      } else {
+        // tile mode (oo_transform): the tile and, in pair-symmetric mode, its transpose, so that
+        // the q-contraction reads both orientations with unit stride
+        double* out = p.Y + (size_t)slab * Np * Np;
+        double* outT = p.YT ? p.YT + (size_t)slab * Np * Np : nullptr;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = 64 * i + 2 * lane + h;
+            const double v = h ? tile[i].y : tile[i].x;
+            if (p.l2_hints & 2) {
+              st_global_hint(out + e, v, keep);
+              if (outT) st_global_hint(outT + (e % Np) * Np + e / Np, v, keep);
+            } else {
+              out[e] = v;
+              if (outT) outT[(e % Np) * Np + e / Np] = v;
+            }
+          }
+        }
       }
+    }
+    return;
+  }
+
+  if (warp > K1_NWARP + 1) {
+    // ------------------------- epilogue warps A, B: the dot products -------------------------
+    // fused mode only: warp A contracts the finished tile with QA_q (row t of A), warp B with
+    // QB_t (row q); 2 x Np doubles per slab leave the SM instead of the tile.
+    if (p.QA == nullptr) return;
+    constexpr int NCH = Np * Np / 64;
+    const bool second = warp == K1_NWARP + 3;
+    const bool active = !second || p.QB != nullptr;
+    const uint64_t keep = l2_policy_evict_last();
+    int it = 0;
+    for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x, ++it) {
+      const int tq = p.slab_tq ? __ldg(p.slab_tq + slab) : slab;
+      const int b = it & 1, n = it >> 1;
+      mbar_wait(tfull_base + 8u * b, (uint32_t)(n & 1));
+      double2 tile[NCH];
+      if (active) {
+        const double2* src = reinterpret_cast<const double2*>(Tbuf + b * Np * Np) + lane;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) tile[i] = src[32 * i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree_base + 8u * b);
+      if (!active) continue;
+      const int tl = tq / p.M, q = tq - tl * p.M;
+      const double* Q = (second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np) +
+                        2 * lane;
+      k1_epilogue_dots<NT>(tile, Q, lane, keep,
+                           p.Aslab + ((size_t)slab * 2 + (second ? 1 : 0)) * Np);
     }
     return;
   }

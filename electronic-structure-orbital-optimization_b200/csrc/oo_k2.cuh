@@ -218,6 +218,185 @@ struct PeerComm {
 
 constexpr int TAIL_THREADS = 256;
 
+// The one-shot all-reduce, executed by all TAIL_THREADS threads of ONE CTA (the last CTA of the
+// tail kernel, after it has written the complete local vector buf[0 .. len)).
+__device__ inline void peer_allreduce_cta(const PeerComm& cm, double* buf, int len) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const unsigned long long seq = *cm.seq_ptr + 1ull;
+  const int par = (int)(seq & 1ull);
+  const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
+  for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+    const double val = __ldcg(buf + idx);
+    for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < cm.world)
+    *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = seq;
+  if (tid < cm.world) {
+    volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
+    const unsigned long long t_start = global_timer_ns();
+    while (*f < seq) {
+      if (global_timer_ns() - t_start > cm.timeout_ns) {   // give up instead of hanging
+        *cm.error_flag = 1;
+        *((volatile int*)cm.error_flag_host) = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // a time-out (now or earlier) means stale slots and ranks that no longer agree bit for bit:
+  // poison the result instead of returning a wrong one
+  const bool poisoned = *((volatile int*)cm.error_flag) != 0;
+  const double* mine_slots = cm.slots[cm.rank] + (size_t)par * cm.world * cm.stride;
+  for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+    double sum = 0.0;
+    for (int r = 0; r < cm.world; ++r) sum += __ldcg(mine_slots + (size_t)r * cm.stride + idx);
+    buf[idx] = poisoned ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+  }
+  __syncthreads();                 // everybody has read *seq_ptr
+  if (tid == 0) *cm.seq_ptr = seq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiles path of the evaluation (N in 25..32, where the fused epilogue of K1 cannot keep up: 2048
+// FP64 instructions per slab for two warps): K1 stores the tiles, k_qcontract builds T3 and
+// k_tail_row contracts it with the 2-RDM.
+// ---------------------------------------------------------------------------------------------
+struct TailParams {
+  PeerComm comm;
+  const double* T3;    // [nrows][Np^3]
+  const double* Gp;    // [Np^3][Np]: 2-RDM, a fastest (see k_prepare_gamma)
+  const double* U;     // [M][N]
+  const double* B1;    // [mloc][N]  one-body rows of the shard
+  const double* B12;   // [mloc][N]
+  double* out;         // [M*N + 1]: gradient rows + energy (rows outside [row0,row0+nrows) untouched)
+  double* rowE;        // [Np/AC][nrows] per-row energy partials
+  unsigned int* counter;
+  const int* done_flag;
+  int M, N, t0, mloc;  // shard: the one-body terms are added for rows in [t0, t0+mloc) only
+  int row0, nrows;
+  double two_body_grad_factor;  // 4 for the one-pass (V4-symmetric) gradient
+  int accumulate;               // 0 (kept for the kernel's generality: out[x] += A[x])
+  int do_step;                  // run the optimiser transition in the last CTA
+  StepParams step;
+};
+
+// Register blocking of the 2-RDM contraction: R rows x AC a-values per CTA (grid.y = Np / AC).
+// The 2-RDM is re-read from L2 once per CTA row-group and the T3 rows once per a-chunk, so the
+// L2 traffic is nrows/R * |Gp| + Np/AC * |T3|; R*AC accumulators live in registers.
+__host__ __device__ constexpr int tail_rows(int NT) { return NT <= 2 ? 4 : 8; }
+__host__ __device__ constexpr int tail_ac(int NT) { return NT >= 1 ? 8 : 8; }
+
+// grid (ceil(nrows / R), Np / AC), block 256.  For the R rows x and the AC values a of the CTA:
+//   A[x][a] = sum_{j,e} T3[x][j][e] * Gp[a][j][e]                                 (2-RDM contraction)
+//   out[x][a] = 4 A[x][a] + B12[x][a] (own rows),   rowE[y][x] = sum_a U[x][a] (A + B1)[x][a]
+// and the last CTA adds rowE in fixed order into out[M*N].
+template <int NT>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_row(const TailParams p) {
+  constexpr int Np = NT * 8, L = Np * Np * Np, NW = TAIL_THREADS / 32, R = tail_rows(NT),
+                AC = tail_ac(NT);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  __shared__ double s_part[NW][R][AC];
+  __shared__ double s_e[R][AC];
+  __shared__ StepSmem sm;
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int xl0 = blockIdx.x * R, a0 = blockIdx.y * AC, N = p.N;
+
+  double acc[R][AC];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int a = 0; a < AC; ++a) acc[r][a] = 0.0;
+  const double* tp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) tp[r] = p.T3 + (size_t)min(xl0 + r, p.nrows - 1) * L;
+  // each thread takes two consecutive (j,e) positions per step: 16-byte loads everywhere
+#pragma unroll 2
+  for (int idx = tid * 2; idx < L; idx += TAIL_THREADS * 2) {
+    double2 tv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) tv[r] = *reinterpret_cast<const double2*>(tp[r] + idx);
+    const double2* g0 = reinterpret_cast<const double2*>(p.Gp + (size_t)idx * Np + a0);
+    const double2* g1 = reinterpret_cast<const double2*>(p.Gp + (size_t)(idx + 1) * Np + a0);
+#pragma unroll
+    for (int a2 = 0; a2 < AC / 2; ++a2) {
+      const double2 u = __ldg(g0 + a2), v = __ldg(g1 + a2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][2 * a2] = fma(tv[r].x, u.x, fma(tv[r].y, v.x, acc[r][2 * a2]));
+        acc[r][2 * a2 + 1] = fma(tv[r].x, u.y, fma(tv[r].y, v.y, acc[r][2 * a2 + 1]));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int a = 0; a < AC; ++a) {
+      double v = acc[r][a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_part[warp][r][a] = v;
+    }
+  __syncthreads();
+  if (tid < R * AC) {
+    const int r = tid / AC, al = tid - r * AC, a = a0 + al;
+    const int xl = xl0 + r, x = p.row0 + xl;
+    double ev = 0.0;
+    if (xl < p.nrows && a < N) {
+      double av = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) av += s_part[w][r][al];
+      const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
+      double b1 = 0.0, b12 = 0.0;
+      if (mine) {
+        b1 = p.B1[(size_t)(x - p.t0) * N + a];
+        b12 = p.B12[(size_t)(x - p.t0) * N + a];
+      }
+      if (p.accumulate) p.out[(size_t)x * N + a] += p.two_body_grad_factor * av;
+      else p.out[(size_t)x * N + a] = p.two_body_grad_factor * av + b12;
+      ev = __ldg(p.U + (size_t)x * N + a) * (av + b1);
+    }
+    s_e[r][al] = ev;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int r = 0; r < R; ++r) {
+      if (xl0 + r < p.nrows) {
+        double e = 0.0;
+        for (int a = 0; a < AC; ++a) e += s_e[r][a];
+        p.rowE[(size_t)blockIdx.y * p.nrows + xl0 + r] = e;
+      }
+    }
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.counter, 1u);
+    is_last = (prev == (unsigned int)(gridDim.x * gridDim.y - 1));
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double v = 0.0;
+    for (int i = tid; i < p.nrows * (int)gridDim.y; i += TAIL_THREADS)
+      v += ((volatile double*)p.rowE)[i];
+    v = block_sum(v, sm.scratch);                  // fixed tree: deterministic
+    if (tid == 0) {
+      if (!p.accumulate) p.out[(size_t)p.M * N] = v;
+      *p.counter = 0u;
+    }
+    if (p.comm.enabled) peer_allreduce_cta(p.comm, p.out, p.M * N + 1);
+    if (p.do_step) {
+      __threadfence();
+      __syncthreads();
+      opt_step_cta<TAIL_THREADS>(p.step, sm);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused evaluation (see oo_k1.cuh): what runs before and after K1.
 // ---------------------------------------------------------------------------------------------
@@ -242,6 +421,7 @@ struct PrepParams {
   const int* done_flag;
   int M, N, t0, mloc;
   int rows_per_chunk;
+  int onebody_only;     // tiles path: only the z = 2 part runs
 };
 
 constexpr int PREP_MAX_ROWS = 16;   // rows of U per CTA of k_prepare_q
@@ -294,7 +474,7 @@ __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
     return;
   }
   const bool second = blockIdx.z == 1;
-  if (second && p.G2B == nullptr) return;
+  if (p.onebody_only || (second && p.G2B == nullptr)) return;
   const int nrows = second ? p.mloc : M;
   const int r0 = blockIdx.y * p.rows_per_chunk, r1 = min(nrows, r0 + p.rows_per_chunk);
   if (r0 >= r1) return;
@@ -453,46 +633,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
       *p.counter = 0u;
     }
   }
-  if (p.comm.enabled) {
-    // ---- fused one-shot all-reduce of out[0 .. M*N] over peer memory (see PeerComm) ----
-    __syncthreads();
-    const PeerComm& cm = p.comm;
-    const unsigned long long seq = *cm.seq_ptr + 1ull;
-    const int len = M * N + 1, par = (int)(seq & 1ull);
-    const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
-    for (int idx = tid; idx < len; idx += TAIL_THREADS) {
-      const double val = __ldcg(p.out + idx);
-      for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < cm.world)
-      *((volatile unsigned long long*)(cm.flags[tid] + par * cm.world + cm.rank)) = seq;
-    if (tid < cm.world) {
-      volatile unsigned long long* f = cm.flags[cm.rank] + par * cm.world + tid;
-      const unsigned long long t_start = global_timer_ns();
-      while (*f < seq) {
-        if (global_timer_ns() - t_start > cm.timeout_ns) {   // give up instead of hanging
-          *cm.error_flag = 1;
-          *((volatile int*)cm.error_flag_host) = 1;
-          break;
-        }
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-    // a time-out (now or earlier) means stale slots and ranks that no longer agree bit for
-    // bit: poison the result instead of returning a wrong one
-    const bool poisoned = *((volatile int*)cm.error_flag) != 0;
-    const double* mine_slots = cm.slots[cm.rank] + (size_t)par * cm.world * cm.stride;
-    for (int idx = tid; idx < len; idx += TAIL_THREADS) {
-      double s = 0.0;
-      for (int r = 0; r < cm.world; ++r) s += __ldcg(mine_slots + (size_t)r * cm.stride + idx);
-      p.out[idx] = poisoned ? __longlong_as_double(0x7ff8000000000000ll) : s;
-    }
-    __syncthreads();                 // everybody has read *seq_ptr
-    if (tid == 0) *cm.seq_ptr = seq;
-  }
+  if (p.comm.enabled) peer_allreduce_cta(p.comm, p.out, M * N + 1);
   if (p.do_step) {
     __threadfence();
     __syncthreads();

@@ -290,3 +290,70 @@ def test_decay_factor_vs_reference_golden():
         assert abs(res["energy"] - float(gold[f"E_{d}"])) <= 1e-8
         counts.append(len(res["callbacks"]))
     assert len(set(counts)) == len(counts)         # the parameter really changes the stopping point
+
+
+def test_patch_reference_routes_rotated_hamiltonian(monkeypatch):
+    """esoo_b200.patch_reference on the LIVE reference class (qiskit mocked, as in ref_loader): the
+    patched BaseOptOrbSolver.get_rotated_hamiltonian hands ElectronicEnergy.from_raw_integrals the
+    same h1_a / h2_aa as the reference's own CPU einsums (base_opt_orb_solver.py:597-612), with the
+    tensors coming from the optimiser's engine (here an oracle-backed stand-in for the CUDA one);
+    solvers whose optimiser is not an esoo_b200 one keep the original method."""
+    import sys
+    import types
+    from unittest import mock
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present on this machine")
+    import esoo_b200
+    from esoo_b200 import ingest
+    _, Base = ref_loader.load_reference()
+    base_mod = sys.modules[Base.__module__]
+    gold = load_golden("rotated_integrals")
+    hs, gs = torch.from_numpy(gold["c_h_spin"]), torch.from_numpy(gold["c_g_spin"])
+    U = torch.from_numpy(gold["c_U"])
+    N = int(gold["c_N"])
+
+    class OracleEngine:                      # what OrbitalEngine.transform returns, from the oracle
+        def __init__(self, h, g):
+            self.h, self.g = h, g
+
+        def transform(self, Ux):
+            h_rot, g_rot = onp.rotated_integrals_spatial(Ux.numpy(), self.h.numpy(), self.g.numpy())
+            return torch.from_numpy(h_rot), torch.from_numpy(g_rot)
+
+    class FakeOptimizer:
+        def _engine_for(self, h, g):
+            h_sp, g_sp, st = ingest.reduce_integrals(h, g)
+            return OracleEngine(h_sp, g_sp), st
+
+    def make_solver(optimizer):
+        sv = Base.__new__(Base)
+        sv.one_body_integrals, sv.two_body_integrals = hs, gs
+        sv.num_spin_orbitals = 2 * N
+        sv.mapper = mock.MagicMock()
+        sv._partial_unitary_optimizer_list = [None, optimizer]
+        return sv
+
+    captured = []
+    fake_ee = mock.MagicMock()
+    fake_ee.from_raw_integrals.side_effect = lambda h1_a, h2_aa: captured.append(
+        (np.array(h1_a), np.array(h2_aa))) or mock.MagicMock()
+    monkeypatch.setattr(base_mod, "ElectronicEnergy", fake_ee)
+    ham_mod = types.ModuleType("qiskit_nature.second_q.hamiltonians")
+    ham_mod.ElectronicEnergy = fake_ee
+    monkeypatch.setitem(sys.modules, "qiskit_nature.second_q.hamiltonians", ham_mod)
+
+    original = Base.get_rotated_hamiltonian
+    make_solver(object()).get_rotated_hamiltonian(U)            # the reference's own einsums
+    try:
+        esoo_b200.patch_reference(Base)
+        make_solver(FakeOptimizer()).get_rotated_hamiltonian(U)  # routed through the engine
+        make_solver(object()).get_rotated_hamiltonian(U)         # foreign optimiser: original path
+    finally:
+        Base.get_rotated_hamiltonian = original
+    assert len(captured) == 3
+    (h_ref, g_ref), (h_new, g_new), (h_old, g_old) = captured
+    assert h_ref.shape == (N, N) and g_ref.shape == (N, N, N, N)
+    assert np.max(np.abs(h_new - h_ref)) <= 1e-12 and np.max(np.abs(g_new - g_ref)) <= 1e-12
+    assert np.array_equal(h_old, h_ref) and np.array_equal(g_old, g_ref)
