@@ -20,7 +20,7 @@ def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
                   if not os.path.basename(p).startswith(("outer_", "bb_update", "opt_decay", "fd_",
-                                                         "rotated_")))
+                                                         "rotated_", "bench_")))
 
 
 def outer_golden_names():
