@@ -350,7 +350,8 @@ int launch_prep_t(oo_ctx* c, const double* U, const int* done_flag, int kindA, i
   chunks = std::max(chunks, (c->mloc + nbx - 1) / nbx);     // z = 2 needs nbx * chunks >= mloc CTAs
   chunks = std::min(chunks, 65535);
   pp.rows_per_chunk = (c->M + chunks - 1) / chunks;
-  CU_TRY(launch_chain(c, k_prepare_q<NT>, dim3(nbx, chunks, 3), dim3(256), 0, pp));
+  CU_TRY(launch_chain(c, k_prepare_q<NT>, dim3(nbx, chunks, 3), dim3(256),
+                      (size_t)2 * c->M * sizeof(double), pp));
   c->launches++;
   return OO_OK;
 }
@@ -428,6 +429,7 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.grad_factor = c->generic ? 1.0 : 4.0;
   tp.accumulate = pass > 0 ? 1 : 0;
   tp.do_step = step != nullptr ? 1 : 0;
+  if (step && c->M * c->N <= STEP_SMALL_MN && getenv("OO_NO_SMALL_STEP") == nullptr) tp.do_step = 2;
   if (step) tp.step = *step;
   CU_TRY(launch_chain(c, k_tail_reduce<NT>, dim3(tp.nrows), dim3(TAIL_THREADS), 0, tp));
   c->launches++;

@@ -316,9 +316,10 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
   pdl_wait();
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   // Transposed, zero-padded copy of U: Ut[l][s] = U[s][l].
+  // (read row-major, i.e. coalesced: consecutive threads take consecutive l of one row s)
   for (int idx = tid; idx < Np * p.upitch; idx += K1_THREADS) {
-    const int l = idx / p.upitch, s = idx - l * p.upitch;
-    Ut[idx] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+    const int s = idx / Np, l = idx - s * Np;
+    Ut[l * p.upitch + s] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
   }
   // Side product for the tail kernels: the zero-padded row-major copy Upad[M][Np].
   if (blockIdx.x == 0 && p.Upad != nullptr) {

@@ -218,15 +218,27 @@ struct PeerComm {
 
 constexpr int TAIL_THREADS = 256;
 
+// One finished element of this GPU's vector straight into the slot of every rank (called by the
+// CTA that produced it; made visible by that CTA's system-scope fence before it reports in).
+__device__ __forceinline__ void peer_push_value(const PeerComm& cm, int idx, double val) {
+  const unsigned long long seq = *cm.seq_ptr + 1ull;
+  const size_t my_slot = ((size_t)(seq & 1ull) * cm.world + cm.rank) * cm.stride;
+  for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
+}
+
 // The one-shot all-reduce, executed by all TAIL_THREADS threads of ONE CTA (the last CTA of the
 // tail kernel, after it has written the complete local vector buf[0 .. len)).
-__device__ inline void peer_allreduce_cta(const PeerComm& cm, double* buf, int len) {
+// `first` = index of the first element this CTA still has to push: 0 pushes the whole vector;
+// len - 1 only the energy, when the CTAs that produced the gradient rows have pushed them
+// themselves (peer_push_row) -- the 7 x 32 KB of remote stores are then spread over all CTAs of
+// the tail kernel instead of being serialised in its last one.
+__device__ inline void peer_allreduce_cta(const PeerComm& cm, double* buf, int len, int first = 0) {
   const int tid = threadIdx.x;
   __syncthreads();
   const unsigned long long seq = *cm.seq_ptr + 1ull;
   const int par = (int)(seq & 1ull);
   const size_t my_slot = ((size_t)par * cm.world + cm.rank) * cm.stride;
-  for (int idx = tid; idx < len; idx += TAIL_THREADS) {
+  for (int idx = first + tid; idx < len; idx += TAIL_THREADS) {
     const double val = __ldcg(buf + idx);
     for (int r = 0; r < cm.world; ++r) cm.slots[r][my_slot + idx] = val;
   }
@@ -435,18 +447,36 @@ __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
   const int tid = threadIdx.x, N = p.N, M = p.M;
   if (blockIdx.z == 2) {
     // ---- one-body rows: B1 = (h U D^T)[x], B12 = B1 + (h^T U D)[x] ----
+    // Pure latency (a 1 x M by M x N product per row): row x and column x of h go to shared
+    // memory in one round trip, then every thread walks its slice of q with 8 loads of U in flight.
     const int ob = blockIdx.y * gridDim.x + blockIdx.x;
     if (ob >= p.mloc) return;
+    extern __shared__ double s_h[];                    // [2][M]: h[x][:], h[:][x]
     __shared__ double s_r1[256], s_r2[256], s_hu[32], s_htu[32];
     const int x = p.t0 + ob;
+    for (int q = tid; q < M; q += 256) {
+      s_h[q] = __ldg(p.h + (size_t)x * M + q);
+      s_h[M + q] = __ldg(p.h + (size_t)q * M + x);
+    }
+    __syncthreads();
     const int j = tid % N, part = tid / N, nparts = 256 / N;
     double r1 = 0.0, r2 = 0.0;
     if (part < nparts) {
-#pragma unroll 4
-      for (int q = part; q < M; q += nparts) {
+      int q = part;
+      for (; q + 7 * nparts < M; q += 8 * nparts) {
+        double u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = __ldg(p.U + (size_t)(q + k * nparts) * N + j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          r1 = fma(s_h[q + k * nparts], u[k], r1);
+          r2 = fma(s_h[M + q + k * nparts], u[k], r2);
+        }
+      }
+      for (; q < M; q += nparts) {
         const double u = __ldg(p.U + (size_t)q * N + j);
-        r1 = fma(__ldg(p.h + (size_t)x * M + q), u, r1);
-        r2 = fma(__ldg(p.h + (size_t)q * M + x), u, r2);
+        r1 = fma(s_h[q], u, r1);
+        r2 = fma(s_h[M + q], u, r2);
       }
     }
     s_r1[tid] = r1;
@@ -534,7 +564,8 @@ struct TailReduceParams {
   int energy_mirror;     // 1: the mirror records enter the energy as well (V4: A is complete)
   double grad_factor;    // 4 for the one-pass V4 gradient, 1 per generic slot pair
   int accumulate;        // generic second pass: out += A, energy untouched
-  int do_step;           // run the optimiser transition in the last CTA
+  int do_step;           // 1: run the optimiser transition in the last CTA; 2: its small-problem
+                         // variant (M*N <= STEP_SMALL_MN)
   StepParams step;
 };
 
@@ -548,7 +579,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
   __shared__ double s_e[Np];
   __shared__ bool is_last;
   __shared__ StepSmem sm;
+  __shared__ StepSmallSmem ss;
   const int tid = threadIdx.x, a = tid % Np, grp = tid / Np, N = p.N, M = p.M;
+  // small problems: every CTA loads what the optimiser transition will need (any of them may be
+  // the last one), in the shadow of the row reduction; OO_NO_STEP_FUSION / large M*N: off
+  const bool small_step = p.do_step == 2;
+  if (small_step) opt_step_small_prefetch<TAIL_THREADS>(p.step, ss);
+  // fused all-reduce: every CTA pushes its own row to the peers when the launch covers all rows
+  // (dense first-index shards leave the other rows to the bulk push of the last CTA: zeros)
+  const bool row_push = p.comm.enabled && p.nrows == M;
   const bool act = grp < G;                 // Np = 24: the last 16 threads have no group
   const int x = p.row0 + blockIdx.x;
   const bool mine = (x >= p.t0) && (x < p.t0 + p.mloc);
@@ -606,8 +645,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
         b1 = p.B1[(size_t)(x - p.t0) * N + tid];
         b12 = p.B12[(size_t)(x - p.t0) * N + tid];
       }
-      if (p.accumulate) p.out[(size_t)x * N + tid] += p.grad_factor * av;
-      else p.out[(size_t)x * N + tid] = p.grad_factor * av + b12;
+      double gval = p.grad_factor * av;
+      if (p.accumulate) gval += p.out[(size_t)x * N + tid];
+      else gval += b12;
+      p.out[(size_t)x * N + tid] = gval;
+      if (row_push) peer_push_value(p.comm, x * N + tid, gval);
       ev = __ldg(p.U + (size_t)x * N + tid) * ((p.energy_mirror ? av : a_own) + b1);
     }
     s_e[tid] = ev;
@@ -617,7 +659,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
     double e = 0.0;
     for (int i = 0; i < Np; ++i) e += s_e[i];
     p.rowE[blockIdx.x] = e;
-    __threadfence();
+    if (row_push) __threadfence_system();   // the remote stores of this row, before reporting in
+    else __threadfence();
     const unsigned int prev = atomicAdd(p.counter, 1u);
     is_last = (prev == (unsigned int)(gridDim.x - 1));
   }
@@ -633,11 +676,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
       *p.counter = 0u;
     }
   }
-  if (p.comm.enabled) peer_allreduce_cta(p.comm, p.out, M * N + 1);
+  if (p.comm.enabled) peer_allreduce_cta(p.comm, p.out, M * N + 1, row_push ? M * N : 0);
   if (p.do_step) {
     __threadfence();
     __syncthreads();
-    opt_step_cta<TAIL_THREADS>(p.step, sm);
+    if (small_step) opt_step_small_cta<TAIL_THREADS>(p.step, sm, ss);
+    else opt_step_cta<TAIL_THREADS>(p.step, sm);
   }
 }
 

@@ -366,49 +366,58 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
   c = scratch3[98];
 }
 
+// The stopping-rule state machine of pupo.py:176-346 (three hand-unrolled iterations, then
+// `while St_array[0] > tol and iteration_number <= maxiter`): given the state before iteration k
+// and f(U_k), the histories after it and whether the loop ends here.
+struct StepDecision {
+  double P0, P1, P2, S0, S1;
+  bool stop;
+};
+__device__ __forceinline__ StepDecision step_decide(const OptState& st, double fk) {
+  StepDecision r{st.P4[0], st.P4[1], st.P4[2], st.S[0], st.S[1], false};
+  const double d = st.decay;
+  const int k = st.k;
+  if (k == 0) {
+    r.P2 = fk;                                          // P4_array[2] = f(U_0)
+  } else if (k == 1) {
+    r.P1 = fk;                                          // P4_array[1] = f(U_1)
+    r.S0 = (1.0 - d) * fabs(r.P1 - r.P2) + d * r.S1;    // S_1, with S1 preset to 1.5*tol
+  } else if (k == 2) {
+    r.P0 = fk;                                          // P4_array[0] = f(U_2)
+    r.S1 = r.S0;                                        // np.roll(St_array, 1) on a 2-vector = swap
+    r.S0 = (1.0 - d) * fabs(r.P0 - r.P1) + d * r.S1;    // S_2
+  } else if (!(r.S0 > st.tol && k <= st.maxiter)) {
+    r.stop = true;
+  } else {
+    r.P2 = r.P1; r.P1 = r.P0; r.P0 = fk;                // roll, then P4_array[0] = f(U_k)
+    const double s_old = r.S0;
+    r.S1 = s_old;
+    r.S0 = (1.0 - d) * fabs(r.P1 - r.P2) + d * r.S1;    // lagged difference, as in the reference
+  }
+  return r;
+}
+
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
 // Called by every thread of ONE CTA of THREADS threads (the stand-alone k_step kernel, or the last
-// CTA of k_tail_reduce when the step is fused into the evaluation's tail).
+// CTA of the tail kernel when the step is fused into the evaluation).
 template <int THREADS>
 __device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
   OptState* st = p.st;
   if (st->done) return;
   const int tid = threadIdx.x, nth = THREADS;
   const int MN = p.M * p.N;
-  const int k = st->k;
+  const OptState s0 = *st;
+  const int k = s0.k;
   const double fk = p.gE[MN];
-  double alpha = st->alpha;
-  double P0 = st->P4[0], P1 = st->P4[1], P2 = st->P4[2], S0 = st->S[0], S1 = st->S[1];
-  const double d = st->decay;
-  bool stop = false;
-
-  if (k == 0) {
-    P2 = fk;                                   // P4_array[2] = f(U_0)
-  } else if (k == 1) {
-    P1 = fk;                                   // P4_array[1] = f(U_1)
-    S0 = (1.0 - d) * fabs(P1 - P2) + d * S1;   // S_1, with S1 preset to 1.5*tol
-  } else if (k == 2) {
-    P0 = fk;                                   // P4_array[0] = f(U_2)
-    S1 = S0;                                   // np.roll(St_array, 1) on a 2-vector = swap
-    S0 = (1.0 - d) * fabs(P0 - P1) + d * S1;   // S_2
-  } else {
-    // `while St_array[0] > tol and iteration_number <= maxiter`
-    if (!(S0 > st->tol && k <= st->maxiter)) {
-      stop = true;
-    } else {
-      P2 = P1; P1 = P0; P0 = fk;               // roll, then P4_array[0] = f(U_k)
-      const double s_old = S0;
-      S1 = s_old;
-      S0 = (1.0 - d) * fabs(P1 - P2) + d * S1; // lagged difference, as in the reference loop body
-    }
-  }
+  double alpha = s0.alpha;
+  const StepDecision dec = step_decide(s0, fk);
   __syncthreads();  // every thread has read the state before thread 0 rewrites it
 
-  if (stop) {
+  if (dec.stop) {
     if (tid == 0) {
       st->done = 1;
       st->k_final = k;
-      st->E_final = P0;                        // reference returns P4_array[0] = f(U_{k-1})
+      st->E_final = dec.P0;                    // reference returns P4_array[0] = f(U_{k-1})
     }
     return;
   }
@@ -437,8 +446,83 @@ __device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
                        sm.cs, sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
   if (tid == 0) {
     st->alpha = alpha;
-    st->P4[0] = P0; st->P4[1] = P1; st->P4[2] = P2;
-    st->S[0] = S0; st->S[1] = S1;
+    st->P4[0] = dec.P0; st->P4[1] = dec.P1; st->P4[2] = dec.P2;
+    st->S[0] = dec.S0; st->S[1] = dec.S1;
+    st->k = k + 1;
+    if (!isfinite(alpha) || !isfinite(fk)) st->nan_flag = 1;
+  }
+}
+
+// The same transition for small problems (M*N <= STEP_SMALL_MN), where the step is pure latency:
+// U_k, U_{k-1}, G_{k-1} and the optimiser state were loaded into shared memory at the START of the
+// tail kernel (in the shadow of the row reduction), G_k is read once, V lives in shared memory, so
+// the chain of dependent global round trips shrinks from seven to one.
+constexpr int STEP_SMALL_MN = 256;
+struct StepSmallSmem {
+  double U[STEP_SMALL_MN], Up[STEP_SMALL_MN], Gp[STEP_SMALL_MN], G[STEP_SMALL_MN];
+  OptState st;
+};
+
+// issued by every thread of every CTA of the tail kernel right after its dependency wait
+template <int THREADS>
+__device__ __forceinline__ void opt_step_small_prefetch(const StepParams& p, StepSmallSmem& ss) {
+  const int MN = p.M * p.N;
+  for (int i = threadIdx.x; i < MN; i += THREADS) {
+    ss.U[i] = p.Ucur[i];
+    ss.Up[i] = p.Uprev[i];
+    ss.Gp[i] = p.Gprev[i];
+  }
+  if (threadIdx.x == 0) ss.st = *p.st;
+}
+
+template <int THREADS>
+__device__ inline void opt_step_small_cta(const StepParams& p, StepSmem& sm, StepSmallSmem& ss) {
+  OptState* st = p.st;
+  const int tid = threadIdx.x, nth = THREADS;
+  const int MN = p.M * p.N;
+  for (int i = tid; i < MN; i += nth) ss.G[i] = p.gE[i];     // the one dependent round trip
+  const double fk = p.gE[MN];
+  __syncthreads();                                           // prefetched data + G visible
+  const OptState s0 = ss.st;
+  if (s0.done) return;
+  const int k = s0.k;
+  double alpha = s0.alpha;
+  const StepDecision dec = step_decide(s0, fk);
+  if (dec.stop) {
+    if (tid == 0) {
+      st->done = 1;
+      st->k_final = k;
+      st->E_final = dec.P0;
+    }
+    return;
+  }
+  if (tid == 0 && k < p.hist_cap) p.E_hist[k] = fk;
+  if (k >= 1) {
+    double uu = 0.0, ug = 0.0, gg = 0.0;
+    for (int i = tid; i < MN; i += nth) {
+      const double du = ss.U[i] - ss.Up[i];
+      const double dg = ss.G[i] - ss.Gp[i];
+      uu = fma(du, du, uu);
+      ug = fma(du, dg, ug);
+      gg = fma(dg, dg, gg);
+    }
+    block_sum3(uu, ug, gg, sm.scratch3);
+    alpha = (k & 1) ? uu / fabs(ug) : fabs(ug) / gg;
+  }
+  // histories to global memory (nobody waits for these stores); V = U_k - alpha G_k over U_{k-1}
+  for (int i = tid; i < MN; i += nth) {
+    const double u = ss.U[i], g = ss.G[i];
+    p.Uprev[i] = u;
+    p.Gprev[i] = g;
+    ss.Up[i] = fma(-alpha, g, u);
+  }
+  __syncthreads();
+  retract_cta<THREADS>(ss.Up, nullptr, 0.0, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3, sm.cs,
+                       sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
+  if (tid == 0) {
+    st->alpha = alpha;
+    st->P4[0] = dec.P0; st->P4[1] = dec.P1; st->P4[2] = dec.P2;
+    st->S[0] = dec.S0; st->S[1] = dec.S1;
     st->k = k + 1;
     if (!isfinite(alpha) || !isfinite(fk)) st->nan_flag = 1;
   }
