@@ -12,7 +12,9 @@ restatement of the reference, oracle/oracle_np.py) and, for the larger shapes, t
   3. the drop-in class itself under torch.distributed: PartialUnitaryProjectionOptimizer shards
      the reference's spin-orbital tensors behind compute_optimal_rotation -- a complete outer loop
      (fixture outer_H4_631G_ground, produced with the live reference optimiser) to 1e-8 Ha, the
-     rotated-Hamiltonian binding, and SpatialIntegrals shards.
+     rotated-Hamiltonian binding, and SpatialIntegrals shards;
+  4. (OO_MG_CONFIG5=1) BASELINE config 5, M=400, N=24, through the class on all GPUs of the box;
+  5. a rank left alone in the fused all-reduce fails with an error and a NaN result (time-out).
 Prints MULTIGPU PASS.
 """
 import os
@@ -213,6 +215,90 @@ def class_cases(rank, world, dev):
     return ok
 
 
+def config5_through_the_class(rank, world, dev):
+    """BASELINE.json configs[4] (M=400, N=24, 204.8 GB dense: needs the GPUs of the box) driven
+    through PartialUnitaryProjectionOptimizer.compute_optimal_rotation with SpatialIntegrals shards.
+    No CPU answer exists at this size (the oracle checks thin M=400 shards in tests/test_gpu_parity);
+    here: the ranks agree bit for bit, the callbacks arrive in order, the energy goes down."""
+    import time
+    M, N, maxiter = 400, 24, 12
+    t0, mloc = esoo_b200.shard_range(M, rank, world)
+    h = synthetic.h_spatial(M)
+    Dsp, Gsp = synthetic.rdms_spin(N)
+    U0 = synthetic.random_partial_unitary(M, N)
+    esoo_b200.clear_engine_cache()
+    g = synthetic.eri_spatial_pair_packed(M, t0, mloc, device=dev)
+    sp = esoo_b200.SpatialIntegrals(g, M, t0=t0, mloc=mloc, packed=True)
+    calls = []
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(1e-4, 0.0, maxiter, device=str(dev),
+                                                      callback=lambda it, e: calls.append((it, e)))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_a = time.perf_counter()
+    U, E = opt.compute_optimal_rotation(fun=_Solver().compute_rotated_energy,
+                                        initial_partial_unitary=U0.clone(), oneRDM=Dsp, twoRDM=Gsp,
+                                        one_body_integrals=h, two_body_integrals=sp)
+    t_first = time.perf_counter() - t_a
+    t_a = time.perf_counter()
+    U2, E2 = opt.compute_optimal_rotation(fun=_Solver().compute_rotated_energy,
+                                          initial_partial_unitary=U0.clone(), oneRDM=Dsp,
+                                          twoRDM=Gsp, one_body_integrals=h, two_body_integrals=sp)
+    t_second = time.perf_counter() - t_a
+    vec = torch.cat([U.reshape(-1), E.reshape(1)]).to(dev)
+    allv = [torch.zeros_like(vec) for _ in range(world)]
+    dist.all_gather(allv, vec)
+    same = all(torch.equal(allv[0], v) for v in allv)
+    Es = [e for _, e in calls]
+    n_it = opt.last_result["n_iter"]
+    good = same and [c[0] for c in calls] == list(range(len(calls))) and n_it == maxiter + 1 and \
+        min(Es) < Es[0] and torch.equal(U, U2) and \
+        float(np.max(np.abs(U.numpy().T @ U.numpy() - np.eye(N)))) <= 1e-12
+    log(rank, f"class config 5 (M={M}, N={N}, {world} GPUs, {g.numel() * 8 / 1e9:.1f} GB/GPU pair-packed): "
+              f"{n_it} iterations, E {Es[0]:.6f} -> {Es[-1]:.6f}, identical on all ranks={same}, "
+              f"first call {t_first:.3f} s, second call (engine cached) {t_second:.3f} s = "
+              f"{n_it / t_second:.1f} iterations/s -> {'ok' if good else 'FAIL'}")
+    esoo_b200.clear_engine_cache()
+    return good
+
+
+def peer_timeout_case(rank, world, dev):
+    """A rank that waits in vain inside the fused all-reduce must fail loudly: rank 0
+    evaluates once more than its peers with a 0.3 s time-out; the call has to raise and the result
+    on the device has to be NaN, never a plausible-looking partial sum."""
+    import time
+    from esoo_b200._lib import OOError
+    M, N = 32, 4
+    t0, mloc = esoo_b200.shard_range(M, rank, world)
+    eng = esoo_b200.OrbitalEngine(M, N, device=dev, t0=t0, mloc=mloc)
+    eng.set_integrals(synthetic.h_spatial(M), synthetic.eri_spatial_shard(M, t0, mloc, device=dev),
+                      assume_v4_symmetric=True)
+    eng.set_rdms(*synthetic.rdms_spatial(N))
+    esoo_b200.attach_nccl(eng)
+    esoo_b200.attach_peer_memory(eng)
+    U = synthetic.random_partial_unitary(M, N)
+    E, _ = eng.energy_grad(U)                       # everybody takes part: fine
+    good = bool(np.isfinite(float(E))) and eng.peer_status() == 1
+    dist.barrier()
+    raised, poisoned = True, True
+    if rank == 0:
+        eng.set_peer_timeout(0.3)
+        raised = False
+        try:
+            eng.energy_grad(U)                      # the peers never come
+        except OOError as exc:
+            raised = "timed out" in str(exc)
+        poisoned = bool(torch.isnan(eng._out).all())
+    else:
+        time.sleep(1.5)
+    dist.barrier()
+    flag = torch.tensor([1 if (good and raised and poisoned) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    log(rank, f"fused all-reduce time-out: call raised={raised}, device result NaN={poisoned} -> "
+              f"{'ok' if int(flag.item()) == 1 else 'FAIL'}")
+    eng.close()
+    return int(flag.item()) == 1
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -222,6 +308,9 @@ def main():
     ok = engine_cases(rank, world, dev)
     if os.environ.get("OO_MG_SKIP_CLASS") is None:
         ok = class_cases(rank, world, dev) and ok
+    if os.environ.get("OO_MG_CONFIG5") is not None:
+        ok = config5_through_the_class(rank, world, dev) and ok
+    ok = peer_timeout_case(rank, world, dev) and ok          # last: it leaves the peers out of step
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
