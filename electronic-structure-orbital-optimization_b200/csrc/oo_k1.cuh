@@ -208,9 +208,12 @@ __device__ __forceinline__ void k1_pass(double (&acc)[K1_RB][NT][2], double (&ya
 //     instead of 8 x 5 (each exchange step halves the number of live values per lane),
 //   * loads in groups of 8, two groups in flight.
 // Fixed shuffle tree => deterministic.
+// q0 = the first load group (a = 0..7, chunk 0), issued by the caller BEFORE it waits for the tile:
+// the slab's (t, q) is known in advance, so one L2 round trip leaves the per-slab critical chain.
 template <int NT>
 __device__ __forceinline__ void k1_epilogue_dots(const double2 (&tile)[NT * NT], const double* Q,
-                                                 int lane, uint64_t keep, double* out) {
+                                                 int lane, uint64_t keep, double* out,
+                                                 const double2 (&q0)[8]) {
   constexpr int Np = NT * 8, Np2 = Np * Np, NCH = Np2 / 64, NAG = Np / 8;
   constexpr int DEPTH = 2;
   static_assert(NCH == NT * NT, "chunks per lane");
@@ -224,12 +227,13 @@ __device__ __forceinline__ void k1_epilogue_dots(const double2 (&tile)[NT * NT],
     const double* Qo = Q + (size_t)o * 8 * Np2;       // NT = 4: this iteration's 8 rows of Q
     double2 qv[DEPTH][8];
     double acc[8];
+    static_assert(DEPTH == 2, "the caller prefetches exactly one group");
+    if (o == 0) {
 #pragma unroll
-    for (int g = 0; g < DEPTH - 1 && g < INNER; ++g) {
-      const int ag = NT <= 3 ? g / NCH : 0, i = g % NCH;
+      for (int a = 0; a < 8; ++a) qv[0][a] = q0[a];
+    } else {
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
-        qv[g % DEPTH][a] = ldg128_hint(Qo + (size_t)(ag * 8 + a) * Np2 + 64 * i, keep);
+      for (int a = 0; a < 8; ++a) qv[0][a] = ldg128_hint(Qo + (size_t)a * Np2, keep);
     }
 #pragma unroll
     for (int g = 0; g < INNER; ++g) {
@@ -437,6 +441,14 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x, ++it) {
       const int tq = p.slab_tq ? __ldg(p.slab_tq + slab) : slab;
       const int b = it & 1, n = it >> 1;
+      const int tl = tq / p.M, q = tq - tl * p.M;
+      const double* Q = (second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np) +
+                        2 * lane;
+      double2 q0[8];
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) q0[a] = ldg128_hint(Q + (size_t)a * Np * Np, keep);
+      }
       mbar_wait(tfull_base + 8u * b, (uint32_t)(n & 1));
       double2 tile[NCH];
       if (active) {
@@ -447,11 +459,8 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tfree_base + 8u * b);
       if (!active) continue;
-      const int tl = tq / p.M, q = tq - tl * p.M;
-      const double* Q = (second ? p.QB + (size_t)tl * Np * Np * Np : p.QA + (size_t)q * Np * Np * Np) +
-                        2 * lane;
       k1_epilogue_dots<NT>(tile, Q, lane, keep,
-                           p.Aslab + ((size_t)slab * 2 + (second ? 1 : 0)) * Np);
+                           p.Aslab + ((size_t)slab * 2 + (second ? 1 : 0)) * Np, q0);
     }
     return;
   }

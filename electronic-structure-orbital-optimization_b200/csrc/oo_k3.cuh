@@ -128,6 +128,93 @@ __device__ inline bool newton_schulz_invsqrt(const double* A, double* Y, double*
   constexpr int LD = K3_NMAX + 1;
   constexpr int EPT = (K3_NMAX * K3_NMAX + THREADS - 1) / THREADS;  // elements per thread
   const int tid = threadIdx.x, nth = blockDim.x, nn = n * n;
+  if (n <= 8) {
+    // Small active spaces (configs 1-3: N = 2, 4): the matrices have at most 64 entries, two per
+    // lane of ONE warp, so the whole iteration runs warp-synchronously (__syncwarp instead of
+    // five CTA-wide barriers per step; the step is pure latency at these sizes).  Same arithmetic
+    // as below; the residual is summed by a fixed shuffle tree.
+    if (tid < 32) {
+      const int lane = tid;
+      double rs = 0.0, dv = 0.0;
+      if (lane < n) {
+        for (int j = 0; j < n; ++j) rs += fabs(A[lane * LD + j]);
+        dv = rs - A[lane * LD + lane] + fabs(A[lane * LD + lane] - 1.0);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+        dv = fmax(dv, __shfl_xor_sync(0xffffffffu, dv, o));
+      }
+      const double cw = dv < 0.5 ? 1.0 : rs;
+      const double inv_cw = 1.0 / cw;
+      int idx2[2], ii[2], jj[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        idx2[k] = lane + 32 * k;
+        ii[k] = idx2[k] / n;
+        jj[k] = idx2[k] - ii[k] * n;
+        if (idx2[k] < nn) {
+          Y[ii[k] * LD + jj[k]] = A[ii[k] * LD + jj[k]] * inv_cw;
+          Z[ii[k] * LD + jj[k]] = (ii[k] == jj[k]) ? 1.0 : 0.0;
+        }
+      }
+      __syncwarp();
+      bool conv = false;
+      int its = 0;
+      for (int it = 0; it < 60; ++it) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (idx2[k] < nn) {
+            double t = 0.0;
+            for (int m = 0; m < n; ++m) t = fma(Z[ii[k] * LD + m], Y[m * LD + jj[k]], t);
+            const double d = t - ((ii[k] == jj[k]) ? 1.0 : 0.0);
+            r = fma(d, d, r);
+            W[ii[k] * LD + jj[k]] = ((ii[k] == jj[k]) ? 3.0 : 0.0) - t;
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        __syncwarp();
+        double yv[2] = {0.0, 0.0}, zv[2] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (idx2[k] < nn) {
+            double sy = 0.0, sz = 0.0;
+            for (int m = 0; m < n; ++m) {
+              sy = fma(Y[ii[k] * LD + m], W[m * LD + jj[k]], sy);
+              sz = fma(W[ii[k] * LD + m], Z[m * LD + jj[k]], sz);
+            }
+            yv[k] = 0.5 * sy;
+            zv[k] = 0.5 * sz;
+          }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (idx2[k] < nn) {
+            Y[ii[k] * LD + jj[k]] = yv[k];
+            Z[ii[k] * LD + jj[k]] = zv[k];
+          }
+        __syncwarp();
+        its = it + 1;
+        if (r < 1e-16) {
+          conv = true;
+          break;
+        }
+      }
+      if (lane == 0) {
+        scratch[0] = conv ? 1.0 : 0.0;
+        scratch[1] = cw;
+        scratch[2] = (double)its;
+      }
+    }
+    __syncthreads();
+    const bool conv_all = scratch[0] != 0.0;
+    const double c_all = scratch[1];
+    if (iters_out) *iters_out = (int)scratch[2];
+    __syncthreads();                       // scratch is reused by the caller's next reduction
+    *inv_sqrt_c = 1.0 / sqrt(c_all);
+    return conv_all;
+  }
   if (tid < n) {
     double s = 0.0;
     for (int j = 0; j < n; ++j) s += fabs(A[tid * LD + j]);
