@@ -44,6 +44,7 @@ constexpr int K1_THREADS = (K1_NWARP + 4) * 32;    // + 1 TMA producer warp + 3 
 constexpr int K1_BAR_FULL = 1;                     // named barrier: per-warp partial tiles written
 constexpr int K1_BAR_FREE = 2;                     // named barrier: partial-tile buffer reusable
 constexpr int K1_BAR_FOLD = 3;                     // first of the two-warp hand-over barriers (ids 3..12)
+constexpr int K1_BAR_UT = 13;                      // U^T built (all warps but the producer)
 constexpr int K1_BAR_COUNT = (K1_NWARP + 1) * 32;  // consumers + the summing epilogue warp
 
 struct K1Params {
@@ -315,24 +316,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
   }
-  // everything above overlaps the tail of the previous kernel (programmatic dependent launch);
-  // U, the Q tensors and the stop flag are its outputs
-  pdl_wait();
-  if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  // Transposed, zero-padded copy of U: Ut[l][s] = U[s][l].
-  // (read row-major, i.e. coalesced: consecutive threads take consecutive l of one row s)
-  for (int idx = tid; idx < Np * p.upitch; idx += K1_THREADS) {
-    const int s = idx / Np, l = idx - s * Np;
-    Ut[l * p.upitch + s] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
-  }
-  // Side product for the tail kernels: the zero-padded row-major copy Upad[M][Np].
-  if (blockIdx.x == 0 && p.Upad != nullptr) {
-    for (int idx = tid; idx < p.M * Np; idx += K1_THREADS) {
-      const int s = idx / Np, l = idx - s * Np;
-      p.Upad[idx] = (l < p.N) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
-    }
-  }
-  __syncthreads();
+  __syncthreads();   // barrier initialisation visible (before any dependency wait: cheap)
 
   const int npass = (p.M + K1_ROWS - 1) / K1_ROWS;
   const int nkc = p.Mk / K1_KC;
@@ -342,14 +326,29 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
 
   if (warp == K1_NWARP) {
     // ------------------------------ TMA producer ------------------------------
+    // The ERI tensor and the slab table do not depend on the previous kernel, so the ring is
+    // filled BEFORE the dependency wait: the first slabs are in flight while the other warps
+    // still wait for U / the Q tensors and build U^T (about 2 us per launch, which is 8 % of an
+    // iteration of the small configs).
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
+      bool checked = p.done_flag == nullptr;     // plain evaluations: nothing to check
+      auto stopped = [&]() {
+        // the optimiser has already stopped: nobody will consume the ring, but the CTA must not
+        // exit while bulk copies into its shared memory are still in flight
+        pdl_wait();
+        checked = true;
+        if (*p.done_flag == 0) return false;
+        for (int s2 = 0; s2 < min(issued, p.nstage); ++s2) mbar_wait(full_base + 8u * s2, 0u);
+        return true;
+      };
       for (int slab = blockIdx.x; slab < p.nslab; slab += gridDim.x) {
         const int coord = p.slab_coord ? __ldg(p.slab_coord + slab) : slab;
         for (int pass = 0; pass < npass; ++pass) {
           for (int kc = 0; kc < nkc; ++kc) {
+            if (!checked && issued == p.nstage && stopped()) return;
             mbar_wait(empty_base + 8u * stage, phase ^ 1u);
             mbar_arrive_expect_tx(full_base + 8u * stage, (uint32_t)p.stage_tx_bytes);
             if (p.l2_hints & 1)
@@ -358,6 +357,7 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
             else
               tma_load_3d(stage_base + (uint32_t)stage * K1_STAGE_BYTES, &tmap, kc * K1_KC,
                           pass * K1_ROWS, coord, full_base + 8u * stage);
+            ++issued;
             if (++stage == p.nstage) {
               stage = 0;
               phase ^= 1u;
@@ -365,8 +365,30 @@ k1_half_transform(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
           }
         }
       }
+      if (!checked) stopped();
     }
     return;
+  }
+
+  // all other warps: U, the Q tensors and the stop flag are outputs of the previous kernels
+  pdl_wait();
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  {
+    // Transposed, zero-padded copy of U: Ut[l][s] = U[s][l]  (read row-major, i.e. coalesced:
+    // consecutive threads take consecutive l of one row s); 11 warps, the producer is busy
+    const int ctid = tid < K1_NWARP * 32 ? tid : tid - 32, cnt = K1_THREADS - 32;
+    for (int idx = ctid; idx < Np * p.upitch; idx += cnt) {
+      const int s = idx / Np, l = idx - s * Np;
+      Ut[l * p.upitch + s] = (l < p.N && s < p.M) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+    }
+    // Side product for the q-contraction (tile mode): the zero-padded row-major copy Upad[M][Np].
+    if (blockIdx.x == 0 && p.Upad != nullptr) {
+      for (int idx = ctid; idx < p.M * Np; idx += cnt) {
+        const int s = idx / Np, l = idx - s * Np;
+        p.Upad[idx] = (l < p.N) ? __ldg(p.U + (size_t)s * p.N + l) : 0.0;
+      }
+    }
+    named_bar_sync(K1_BAR_UT, K1_THREADS - 32);
   }
 
   if (warp == K1_NWARP + 1) {
