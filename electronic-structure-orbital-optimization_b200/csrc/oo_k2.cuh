@@ -438,6 +438,14 @@ struct PrepParams {
 
 constexpr int PREP_MAX_ROWS = 16;   // rows of U per CTA of k_prepare_q
 
+// Does position idx = a*Np^2 + e1*Np + e0 of a Q matrix carry data (a, e0, e1 < N)?
+template <int NT>
+__device__ __forceinline__ bool prep_position_live(int idx, int N) {
+  constexpr int Np = NT * 8;
+  const int a = idx / (Np * Np), e = idx - a * Np * Np, e1 = e / Np, e0 = e - e1 * Np;
+  return a < N && e0 < N && e1 < N;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
   constexpr int Np = NT * 8, Np2 = Np * Np, Np3 = Np2 * Np;
@@ -517,7 +525,8 @@ __global__ void __launch_bounds__(256) k_prepare_q(const PrepParams p) {
     reinterpret_cast<double*>(&s_u[r][0])[c] = c < N ? __ldg(Urow + (size_t)r * N + c) : 0.0;
   }
   const int idx = blockIdx.x * 256 + tid;             // (a, e) position
-  const bool valid = idx < Np3;
+  // positions in the padding (a, k or l >= N) are zero from the allocation and stay zero
+  const bool valid = idx < Np3 && prep_position_live<NT>(idx, N);
   const double* G2 = second ? p.G2B : p.G2A;
   double coef[Np];
 #pragma unroll

@@ -239,6 +239,8 @@ def config5_through_the_class(rank, world, dev):
                                         initial_partial_unitary=U0.clone(), oneRDM=Dsp, twoRDM=Gsp,
                                         one_body_integrals=h, two_body_integrals=sp)
     t_first = time.perf_counter() - t_a
+    first_calls = list(calls)
+    calls.clear()
     t_a = time.perf_counter()
     U2, E2 = opt.compute_optimal_rotation(fun=_Solver().compute_rotated_energy,
                                           initial_partial_unitary=U0.clone(), oneRDM=Dsp,
@@ -250,7 +252,8 @@ def config5_through_the_class(rank, world, dev):
     same = all(torch.equal(allv[0], v) for v in allv)
     Es = [e for _, e in calls]
     n_it = opt.last_result["n_iter"]
-    good = same and [c[0] for c in calls] == list(range(len(calls))) and n_it == maxiter + 1 and \
+    good = same and [c[0] for c in calls] == list(range(maxiter + 1)) and calls == first_calls and \
+        n_it == maxiter + 1 and \
         min(Es) < Es[0] and torch.equal(U, U2) and \
         float(np.max(np.abs(U.numpy().T @ U.numpy() - np.eye(N)))) <= 1e-12
     log(rank, f"class config 5 (M={M}, N={N}, {world} GPUs, {g.numel() * 8 / 1e9:.1f} GB/GPU pair-packed): "
