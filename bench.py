@@ -424,7 +424,7 @@ def main():
     e2e_sync_value = K / float(sync_t.item())
 
     # ---------------- whole inner loop on the device (eval + all-reduce + retraction + BB + stop) --
-    n_inner = max(10, min(K, 50))
+    n_inner = 60
     barrier()
     t_c = time.perf_counter()
     res = eng.optimize(U_host[0], 1e-3, 0.0, n_inner)      # tol=0: runs until iteration > maxiter
