@@ -670,7 +670,7 @@ int ensure_slots(oo_ctx* c) {
 extern "C" {
 
 const char* oo_last_error(void) { return g_last_error.c_str(); }
-const char* oo_version(void) { return "oo_b200 0.1 (sm_100a)"; }
+const char* oo_version(void) { return "oo_b200 0.2 (sm_100a)"; }
 
 int oo_device_count(void) {
   int n = 0;

@@ -40,7 +40,10 @@ def main():
     t0 = time.time()
     res = harness.run_outer_loop(optimizer, hs, gs, 2 * N, mol["n_alpha"], mol["n_beta"],
                                  maxiter=20, stopping_tolerance=1e-5, n_states=args.states,
-                                 outer_loop_callback=outer_cb)
+                                 outer_loop_callback=outer_cb,
+                                 # rotated Hamiltonian (base_opt_orb_solver.py:597-604) from the
+                                 # optimiser's device-resident engine instead of the CPU einsums
+                                 engine_for_transform=optimizer)
     final = res["energies"][-1]
     print("final electronic energy " + ", ".join(f"{e:.8f}" for e in final) +
           f"  (total {final[0] + mol['e_nuc']:.8f}) after {res['outer_iterations']} outer "

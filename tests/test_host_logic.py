@@ -381,3 +381,58 @@ def test_pair_packed_slab_list_and_generator():
     packed = synthetic.eri_spatial_pair_packed(M, t0, mloc)
     ref = torch.stack([g[t - t0, q] for t, q in distributed.pair_slab_list(M, t0, mloc)])
     assert torch.equal(packed, ref)
+
+
+def test_spatial_integrals_and_checksum_host_logic():
+    """Extension input format and the engine-cache fingerprint (no GPU needed)."""
+    import esoo_b200
+    from esoo_b200 import ingest, optimizer as om, synthetic
+    M = 6
+    g = synthetic.eri_spatial(M)
+    sp = esoo_b200.SpatialIntegrals(g, M)
+    assert (sp.t0, sp.mloc, sp.packed, sp.v4_symmetric) == (0, M, False, True)
+    assert sorted(sp.structure.blocks) == [(0, 0, 0, 0), (0, 1, 1, 0), (1, 0, 0, 1), (1, 1, 1, 1)]
+    assert sorted(esoo_b200.SpatialIntegrals(g, M, pattern="abab").structure.blocks) == \
+        [(0, 0, 0, 0), (0, 1, 0, 1), (1, 0, 1, 0), (1, 1, 1, 1)]
+    # the block mask that selects the 2-RDM blocks matches what the spin-orbital ingest detects
+    hs, gs = synthetic.spin_orbital_integrals(synthetic.h_spatial(M), g, "abba")
+    assert ingest.block_mask(sp.structure) == ingest.block_mask(ingest.reduce_integrals(hs, gs)[2])
+    with pytest.raises(ValueError):
+        esoo_b200.SpatialIntegrals(g, M, pattern="aabb")
+    with pytest.raises(ValueError):
+        esoo_b200.SpatialIntegrals(g, M, packed=True, v4_symmetric=False)
+    with pytest.raises(ValueError):                  # a non-symmetric shard needs the transposed rows
+        esoo_b200.SpatialIntegrals(g[:3], M, t0=0, mloc=3, v4_symmetric=False)
+    # fingerprint: full mode sees one changed element and a permutation, sample mode may not
+    a = torch.randn(7, 5, 5, 5, dtype=torch.float64)
+    b = a.clone()
+    b[3, 2, 1, 4] += 1e-12
+    assert om.content_checksum(a) != om.content_checksum(b)
+    assert om.content_checksum(a) != om.content_checksum(a.transpose(1, 2).contiguous())
+    assert om.content_checksum(a) == om.content_checksum(a.clone())
+    assert om.content_checksum(a, sample=True) == om.content_checksum(b, sample=True)   # blind spot
+    with pytest.raises(ValueError):
+        esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0",
+                                                    cache_check="maybe")
+    opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0",
+                                                      distributed=False)
+    assert opt._ranks() == (0, 1)
+    with pytest.raises(RuntimeError):
+        esoo_b200.PartialUnitaryProjectionOptimizer(0.1, 1e-6, 10, device="cuda:0",
+                                                    distributed=True)._ranks()
+
+
+def test_expand_spin_blocks_layout():
+    """Spatial h', g' -> the reference's spin-blocked Q^4 layout (base_opt_orb_solver.py:597-612)."""
+    from esoo_b200 import ingest, rotated
+    N = 3
+    h = torch.arange(N * N, dtype=torch.float64).reshape(N, N)
+    g = torch.arange(N ** 4, dtype=torch.float64).reshape(N, N, N, N) + 1.0
+    st = ingest.SpinStructure(M=5, blocks=[(0, 0, 0, 0), (0, 1, 1, 0), (1, 0, 0, 1), (1, 1, 1, 1)])
+    hs, gs = rotated.expand_spin_blocks(h, g, st)
+    assert hs.shape == (2 * N, 2 * N) and gs.shape == (2 * N,) * 4
+    assert np.array_equal(hs[:N, :N], h.numpy()) and np.array_equal(hs[N:, N:], h.numpy())
+    assert not hs[:N, N:].any() and not hs[N:, :N].any()
+    assert np.array_equal(gs[:N, N:, N:, :N], g.numpy()) and np.array_equal(gs[N:, N:, N:, N:], g.numpy())
+    assert not gs[:N, N:, :N, N:].any()              # (a,b,a,b) is not a block of this pattern
+    assert np.count_nonzero(gs) == 4 * N ** 4
