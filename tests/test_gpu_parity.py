@@ -18,10 +18,11 @@ pytestmark = pytest.mark.gpu
 E_TOL = 1e-10
 G_RTOL = 1e-9
 EFINAL_TOL = 1e-8
-# whole trajectories (up to 445 BB steps) against the live reference / the oracle: bounds = 10x the
-# largest deviation measured on the B200 over all fixtures (profiles/r02_parity_deviations.jsonl:
-# callback energies 7.9e-12 relative, final U 5.4e-11, final energy 2.8e-14)
-TRAJ_E_RTOL = 1e-10
+# whole trajectories (up to 445 BB steps) against the live reference / the oracle: bounds = 10-20x
+# the largest deviation measured on the B200 over all fixtures and over the kernel versions of the
+# round (profiles/r02_parity_deviations.jsonl: callback energies 7.9e-12 .. 1.0e-11 relative, final
+# U 3.0e-12 .. 5.4e-11, final energy 2.8e-14); round 1 accepted 1e-7 / 1e-5
+TRAJ_E_RTOL = 2e-10
 TRAJ_U_TOL = 1e-9
 
 
