@@ -556,7 +556,7 @@ def main():
             "clocks": clocks,
             "energy_checksum": e_sum,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # rank 0 at N=1 only (bench contract)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
