@@ -122,7 +122,7 @@ struct oo_ctx {
   alignas(64) CUtensorMap tmap;
   // workspaces (device)
   double *Y = nullptr, *T3 = nullptr, *D = nullptr, *rowE = nullptr, *out = nullptr, *Ucur = nullptr, *Uprev = nullptr,
-         *Gprev = nullptr, *Vtmp = nullptr, *E_hist = nullptr, *alpha_tmp = nullptr,
+         *Gprev = nullptr, *E_hist = nullptr,
          *YT = nullptr, *Upad = nullptr, *B1 = nullptr, *B12 = nullptr, *Gtmp = nullptr;
   int hist_cap = 0;
   unsigned int* counter = nullptr;
@@ -757,8 +757,6 @@ int oo_create(int device, int M, int N, int t0, int mloc, oo_ctx** out) {
   A(&c->Ucur, MN);
   A(&c->Uprev, MN);
   A(&c->Gprev, MN);
-  A(&c->Vtmp, MN);
-  A(&c->alpha_tmp, 4);
   {
     // slab tables of the pair-symmetric mode (closed forms: pair_row_count / pair_ith_q)
     std::vector<int> coord, rowstart(mloc, 0);
@@ -847,7 +845,7 @@ int oo_destroy(oo_ctx* c) {
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->peer_seq_dev) cudaFree(c->peer_seq_dev);
   double* bufs[] = {c->Y,   c->T3,   c->D,     c->rowE,
-                    c->out, c->Ucur, c->Uprev, c->Gprev, c->Vtmp, c->E_hist, c->alpha_tmp,
+                    c->out, c->Ucur, c->Uprev, c->Gprev, c->E_hist,
                     c->YT,  c->Upad, c->B1,    c->B12,   c->Gtmp};
   for (double* b : bufs)
     if (b) cudaFree(b);
@@ -1184,7 +1182,6 @@ int oo_bb_update(oo_ctx* c, int iteration, const double* U_cur_dev, const double
   p.Gcur = G_cur_dev;
   p.Gprev = G_prev_dev;
   p.Unew = U_new_dev;
-  p.Vtmp = c->Vtmp;
   p.alpha_io = alpha_io_dev;
   p.iteration = iteration;
   p.M = c->M;
@@ -1231,7 +1228,6 @@ int oo_optimize(oo_ctx* c, double* U_io_host, double bb0, double tol, int maxite
   sp.Uprev = c->Uprev;
   sp.gE = c->out;
   sp.Gprev = c->Gprev;
-  sp.Vtmp = c->Vtmp;
   sp.E_hist = c->E_hist;
   sp.M = c->M;
   sp.N = c->N;

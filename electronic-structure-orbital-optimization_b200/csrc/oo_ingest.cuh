@@ -1,5 +1,6 @@
 // Input preparation kernels: permutation-symmetry verification of the ERI tensor and the
-// symmetrised / padded / permuted copy of the 2-RDM consumed by k_tail_row, spin-orbital ingest.
+// symmetrised / padded / permuted copies of the 2-RDM (k_prepare_gamma2 for the fused evaluation,
+// k_prepare_gamma for the tiles path), spin-orbital ingest, pair-packing.
 #pragma once
 #include "oo_common.cuh"
 

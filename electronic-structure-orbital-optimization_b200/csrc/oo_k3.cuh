@@ -400,7 +400,6 @@ struct StepParams {
   double* Uprev;        // U_{k-1}    -> becomes U_k
   const double* gE;     // [M*N+1] gradient at U_k and f(U_k) (already all-reduced)
   double* Gprev;        // G_{k-1}    -> becomes G_k
-  double* Vtmp;         // scratch M*N
   double* E_hist;       // E_hist[k] = f(U_k)
   int M, N;
   int hist_cap;
@@ -632,7 +631,7 @@ __global__ void k_force_stop(OptState* st) {
 // Standalone BB update (compute_updated_partial_unitary, pupo.py:129-159) for API parity.
 struct BBParams {
   const double* Ucur; const double* Uprev; const double* Gcur; const double* Gprev;
-  double* Unew; double* Vtmp; double* alpha_io; int iteration; int M, N; int force_jacobi;
+  double* Unew; double* alpha_io; int iteration; int M, N; int force_jacobi;
 };
 __global__ void __launch_bounds__(K3_THREADS) k_bb_update(const BBParams p) {
   __shared__ double sA[K3_NMAX * (K3_NMAX + 1)], sB1[K3_NMAX * (K3_NMAX + 1)],
