@@ -187,6 +187,38 @@ def class_cases(rank, world, dev):
         log(rank, f"class compute_optimal_rotation {name}: {len(calls)} callbacks, dE={dE:.2e} "
                   f"dU={dU:.2e} -> {'ok' if good else 'FAIL'}")
         ok = ok and good
+    # ---- spin-orbital tensors WITHOUT V4 symmetry through the sharded class (generic path) ----
+    M, N = 10, 3
+    if world <= M:
+        gen = torch.Generator().manual_seed(21)
+        g_gen = 0.1 * torch.randn(M, M, M, M, generator=gen, dtype=torch.float64)
+        h_gen = torch.randn(M, M, generator=gen, dtype=torch.float64)
+        h_gen = 0.5 * (h_gen + h_gen.T)
+        hs, gs = synthetic.spin_orbital_integrals(h_gen, g_gen, "abba")
+        Dsp, Gsp = synthetic.rdms_spin(N, seed=31)
+        D, G = synthetic.rdms_spatial(N, seed=31)
+        U0 = synthetic.random_partial_unitary(M, N, seed=41)
+        hn, gn, Dn, Gn = (t.numpy() for t in (h_gen, g_gen, D, G))
+        ref = onp.optimal_rotation(lambda X: onp.rotated_energy_spatial(X, Dn, Gn, hn, gn),
+                                   lambda X: onp.rotated_energy_grad_spatial(X, Dn, Gn, hn, gn),
+                                   U0.numpy(), 0.01, 1e-9, 40)
+        for where in ("cpu", dev):
+            esoo_b200.clear_engine_cache()
+            opt = esoo_b200.PartialUnitaryProjectionOptimizer(0.01, 1e-9, 40, device=str(dev))
+            U, E = opt.compute_optimal_rotation(fun=_Solver().compute_rotated_energy,
+                                                initial_partial_unitary=U0.clone(), oneRDM=Dsp,
+                                                twoRDM=Gsp, one_body_integrals=hs.to(where),
+                                                two_body_integrals=gs.to(where))
+            from esoo_b200 import optimizer as om
+            entry = next(iter(om._ENGINE_CACHE.values()))
+            dE = abs(float(E) - ref["energy"])
+            dU = float(np.max(np.abs(U.numpy() - ref["U"])))
+            good = entry.engine.generic and entry.engine.mloc < M and dE <= EFINAL_TOL and \
+                opt.last_result["n_iter"] == ref["n_iter"] and dU <= 1e-6
+            log(rank, f"class generic (no V4 symmetry) M={M} N={N}, tensors on {where}: n_iter="
+                      f"{opt.last_result['n_iter']}/{ref['n_iter']} dE={dE:.2e} dU={dU:.2e} -> "
+                      f"{'ok' if good else 'FAIL'}")
+            ok = ok and good
     # ---- SpatialIntegrals shards (the format of configs 4 and 5), pair-packed ----
     M, N = 48, 8
     t0, mloc = esoo_b200.shard_range(M, rank, world)
