@@ -977,3 +977,28 @@ def test_step_fusion_matches_separate_step(torch_cuda, monkeypatch):
     assert runs[0]["n_iter"] == runs[1]["n_iter"]
     assert abs(runs[0]["energy"] - runs[1]["energy"]) <= 1e-10
     assert np.max(np.abs(runs[0]["U"] - runs[1]["U"])) <= 1e-8
+
+
+@pytest.mark.parametrize("M,N", [(30, 26), (40, 32)])
+def test_optimize_on_the_tiles_path_vs_oracle(torch_cuda, M, N):
+    """N in 25..32 keeps the stored-tiles evaluation (k_qcontract + k_tail_row, DESIGN section 3);
+    the optimiser transition is fused into k_tail_row's last CTA there: same trajectory as the
+    oracle's restatement of pupo.py:161-350."""
+    import esoo_b200
+    from oracle import oracle_np as onp
+    torch = torch_cuda
+    h, g, D, G, U = _spatial_case(torch, M, N, seed=M)
+    eng = esoo_b200.OrbitalEngine(M, N, device="cuda:0")
+    eng.set_integrals(h, g)
+    eng.set_rdms(D, G)
+    res = eng.optimize(U.numpy(), 0.01, 1e-9, 30)
+    hn, gn, Dn, Gn = h.numpy(), g.numpy(), D.numpy(), G.numpy()
+    ref = onp.optimal_rotation(lambda X: onp.rotated_energy_spatial(X, Dn, Gn, hn, gn),
+                               lambda X: onp.rotated_energy_grad_spatial(X, Dn, Gn, hn, gn),
+                               U.numpy(), 0.01, 1e-9, 30)
+    record_deviation(f"tiles_path_optimize:{M}x{N}", dE_final=abs(res["energy"] - ref["energy"]),
+                     dU=np.max(np.abs(res["U"] - ref["U"])))
+    assert res["n_iter"] == ref["n_iter"]
+    assert abs(res["energy"] - ref["energy"]) <= EFINAL_TOL * max(1.0, abs(ref["energy"]))
+    assert np.max(np.abs(res["U"] - ref["U"])) <= 1e-8
+    eng.close()
