@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(QC_THREADS, NT <= 2 ? 2 : 1) k_qcontract(const
 // One-shot all-reduce over NVLink peer memory, fused into the last CTA of k_tail_reduce.
 // Every GPU owns a buffer  flags[2][world] | slots[2][world][stride]  that its peers map through
 // CUDA IPC.  Evaluation number `seq` (same on all ranks) uses parity seq&1:
-//   push   my (gradient | energy) vector into slot [parity][my_rank] of EVERY rank (remote stores)
+//   push   my (gradient | energy) vector into slot [parity][my_rank] of EVERY rank (remote stores;
+//          the gradient rows by the CTAs that produce them, the energy by the last CTA)
 //   signal flags[parity][my_rank] = seq on every rank (after a system-scope fence)
 //   wait   until my own flags[parity][r] >= seq for all r
 //   sum    my slots[parity][0..world) in rank order -> identical bits on every rank.
@@ -230,7 +231,7 @@ __device__ __forceinline__ void peer_push_value(const PeerComm& cm, int idx, dou
 // tail kernel, after it has written the complete local vector buf[0 .. len)).
 // `first` = index of the first element this CTA still has to push: 0 pushes the whole vector;
 // len - 1 only the energy, when the CTAs that produced the gradient rows have pushed them
-// themselves (peer_push_row) -- the 7 x 32 KB of remote stores are then spread over all CTAs of
+// themselves (peer_push_value) -- the 7 x 32 KB of remote stores are then spread over all CTAs of
 // the tail kernel instead of being serialised in its last one.
 __device__ inline void peer_allreduce_cta(const PeerComm& cm, double* buf, int len, int first = 0) {
   const int tid = threadIdx.x;
