@@ -128,6 +128,47 @@ def content_checksum(t: torch.Tensor, sample: bool = False) -> Tuple[float, floa
     return float(torch.dot(torch.mv(mat, w2), w1)), float(flat.abs().sum())
 
 
+def plan_sharded_ingest(h_src: torch.Tensor, g_src: torch.Tensor, rank: int, world: int, dev):
+    """Host-side plan of one rank of a sharded run (collective over torch.distributed, any backend):
+    which rows of the first ERI index it keeps, the spin-block structure all ranks agree on, and
+    how the shard will be stored:
+
+        'packed'   V4-symmetric on every rank's rows, even M: pair-packed (half the memory)
+        'dense'    V4-symmetric, odd M (padded): dense rows, symmetry asserted
+        'generic'  not symmetric on some rank: dense rows + the rows of the pair-transposed tensor
+
+    Returns dict(t0, mloc, h, g_rows, structure, storage, g_pair_transposed).  g_rows is on `dev`
+    when the spin-orbital tensor was (device ingest kernel), else on the host."""
+    import torch.distributed as dist
+    M = g_src.shape[0] // 2
+    t0, mloc = dist_mod.shard_range(M, rank, world)
+    if g_src.is_cuda:
+        h_sp, g_rows, structure = ingest.reduce_integrals_device(h_src.to(dev), g_src.to(dev),
+                                                                 t0=t0, mloc=mloc, pad_even=True)
+    else:
+        h_sp, g_rows, structure = ingest.reduce_integrals_rows_host(h_src, g_src, t0, mloc)
+    comm_dev = dev if dist.get_backend() == "nccl" else "cpu"
+    mask = torch.tensor([ingest.block_mask(structure)], dtype=torch.int64, device=comm_dev)
+    lo, hi = mask.clone(), mask.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if int(lo.item()) != int(hi.item()):
+        raise NotImplementedError("the ranks see different non-zero spin blocks of g")
+    ref_block = structure.blocks[0] if structure.blocks else (0, 0, 0, 0)
+    asym, gmax = ingest.v4_asymmetry_rows(g_src, M, ref_block, t0, mloc)
+    flag = torch.tensor([1 if asym <= 1e-11 * max(gmax, 1e-300) else 0], dtype=torch.int64,
+                        device=comm_dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    g_pt = None
+    if int(flag.item()) == 1:
+        storage = "packed" if M % 2 == 0 else "dense"
+    else:
+        storage = "generic"
+        g_pt = ingest._blk(g_src, M, ref_block).permute(2, 3, 0, 1)[t0:t0 + mloc].contiguous()
+    return {"t0": t0, "mloc": mloc, "h": h_sp, "g_rows": g_rows, "structure": structure,
+            "storage": storage, "g_pair_transposed": g_pt}
+
+
 class PartialUnitaryProjectionOptimizer:
     """Gradient-projection optimiser over M x N real partial unitaries with alternating
     Barzilai-Borwein step (reference: partial_unitary_projection_optimizer.py:7)."""
@@ -224,11 +265,8 @@ class PartialUnitaryProjectionOptimizer:
     def _engine_from_spin(self, h_src: torch.Tensor, g_src: torch.Tensor, rank: int, world: int):
         """Spin-orbital tensors (host or device) -> engine holding this rank's rows of the spatial
         block; the M^4 spatial tensor is only materialised on a single-GPU run."""
-        import torch.distributed as dist
         dev = self._torch_device()
-        P = g_src.shape[0]
-        M = P // 2
-        t0, mloc = dist_mod.shard_range(M, rank, world)
+        M = g_src.shape[0] // 2
         if world == 1:
             h_dev, g_dev = h_src.to(dev), g_src.to(dev)
             h_sp, g_sp, structure = ingest.reduce_integrals_device(h_dev, g_dev, pad_even=True)
@@ -237,37 +275,17 @@ class PartialUnitaryProjectionOptimizer:
             eng.set_integrals(h_sp, g_sp)               # verifies V4 on the device; generic else
             return eng, structure
         # ---- sharded: every rank reads only its rows --------------------------------------
-        if g_src.is_cuda:
-            h_sp, g_rows, structure = ingest.reduce_integrals_device(h_src.to(dev), g_src.to(dev),
-                                                                     t0=t0, mloc=mloc,
-                                                                     pad_even=True)
+        plan = plan_sharded_ingest(h_src, g_src, rank, world, dev)
+        h_sp, g_rows, structure = plan["h"], plan["g_rows"], plan["structure"]
+        eng = OrbitalEngine(M, self._n_active, device=dev, t0=plan["t0"], mloc=plan["mloc"])
+        if plan["storage"] == "packed":
+            packed = eng.pack_pair_slabs(g_rows.to(dev))     # half the residency, same traffic
+            del g_rows
+            eng.set_integrals_packed(h_sp, packed)
+        elif plan["storage"] == "dense":
+            eng.set_integrals(h_sp, g_rows, assume_v4_symmetric=True)
         else:
-            h_sp, g_rows, structure = ingest.reduce_integrals_rows_host(h_src, g_src, t0, mloc)
-            g_rows = g_rows.to(dev)
-        mask = torch.tensor([ingest.block_mask(structure)], dtype=torch.int64,
-                            device=dev if dist.get_backend() == "nccl" else "cpu")
-        lo, hi = mask.clone(), mask.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if int(lo.item()) != int(hi.item()):
-            raise NotImplementedError("the ranks see different non-zero spin blocks of g")
-        ref_block = structure.blocks[0] if structure.blocks else (0, 0, 0, 0)
-        asym, gmax = ingest.v4_asymmetry_rows(g_src, M, ref_block, t0, mloc)
-        flag = torch.tensor([1 if asym <= 1e-11 * max(gmax, 1e-300) else 0], dtype=torch.int64,
-                            device=mask.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        eng = OrbitalEngine(M, self._n_active, device=dev, t0=t0, mloc=mloc)
-        if int(flag.item()) == 1:
-            if M % 2 == 0:
-                packed = eng.pack_pair_slabs(g_rows)    # half the residency, same traffic
-                del g_rows
-                eng.set_integrals_packed(h_sp, packed)
-            else:
-                eng.set_integrals(h_sp, g_rows, assume_v4_symmetric=True)
-        else:
-            blk = ingest._blk(g_src, M, ref_block)
-            g_pt = blk.permute(2, 3, 0, 1)[t0:t0 + mloc].contiguous().to(dev)
-            eng.set_integrals(h_sp, g_rows, g_pair_transposed=g_pt)
+            eng.set_integrals(h_sp, g_rows, g_pair_transposed=plan["g_pair_transposed"])
         self._attach(eng, world)
         return eng, structure
 

@@ -276,6 +276,25 @@ def _gloo_worker(rank, world, port, q):
     dist.all_reduce(t2)
     ok = ok and abs(t2[M * N].item() - E_ref) < 1e-12 and \
         np.max(np.abs(t2[:M * N].numpy().reshape(M, N) - g_ref)) < 1e-12
+    # the plan the drop-in class follows under torch.distributed (optimizer.plan_sharded_ingest)
+    from esoo_b200 import optimizer as om
+    plan = om.plan_sharded_ingest(hs, gs, rank, world, "cpu")
+    ok = ok and plan["storage"] == "dense" and (plan["t0"], plan["mloc"]) == (t0, mloc) and \
+        np.array_equal(plan["g_rows"].numpy(), g[rows])                 # M = 11 is odd: padded dense
+    M2 = 8
+    h8, g8 = synthetic.h_spatial(M2), synthetic.eri_spatial(M2)
+    hs8, gs8 = synthetic.spin_orbital_integrals(h8, g8, "abab")
+    t8, m8 = distributed.shard_range(M2, rank, world)
+    plan = om.plan_sharded_ingest(hs8, gs8, rank, world, "cpu")
+    ok = ok and plan["storage"] == "packed" and plan["g_pair_transposed"] is None and \
+        sorted(plan["structure"].blocks) == [(0, 0, 0, 0), (0, 1, 0, 1), (1, 0, 1, 0), (1, 1, 1, 1)]
+    g_ns = g8.clone()
+    g_ns[M2 - 1, 0, 1, 2] += 0.25        # ONE rank sees an asymmetric row: all ranks must go generic
+    hs_ns, gs_ns = synthetic.spin_orbital_integrals(h8, g_ns, "abba")
+    plan = om.plan_sharded_ingest(hs_ns, gs_ns, rank, world, "cpu")
+    ok = ok and plan["storage"] == "generic" and \
+        torch.equal(plan["g_pair_transposed"], g_ns.permute(2, 3, 0, 1)[t8:t8 + m8].contiguous()) and \
+        torch.equal(plan["g_rows"], g_ns[t8:t8 + m8])
     # pair-packed slab lists of the shards partition the full list
     mine = distributed.pair_slab_list(M, t0, mloc)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
