@@ -431,7 +431,23 @@ int launch_tail_t(oo_ctx* c, const double* U, double* out, const int* done_flag,
   tp.do_step = step != nullptr ? 1 : 0;
   if (step && c->M * c->N <= STEP_SMALL_MN && getenv("OO_NO_SMALL_STEP") == nullptr) tp.do_step = 2;
   if (step) tp.step = *step;
-  CU_TRY(launch_chain(c, k_tail_reduce<NT>, dim3(tp.nrows), dim3(TAIL_THREADS), 0, tp));
+  // V of the optimiser transition in dynamic shared memory (see opt_step_cta) when it fits
+  size_t dyn = 0;
+  {
+    const size_t need = (size_t)c->M * c->N * sizeof(double);
+    static const bool off = getenv("OO_NO_STEP_SMEM") != nullptr;
+    if (tp.do_step == 1 && !off && need <= (size_t)100 * 1024) {
+      static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+      if (!attr_set[c->device & 7]) {
+        CU_TRY(cudaFuncSetAttribute(k_tail_reduce<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    100 * 1024));
+        attr_set[c->device & 7] = true;
+      }
+      dyn = need;
+      tp.step_smem = 1;
+    }
+  }
+  CU_TRY(launch_chain(c, k_tail_reduce<NT>, dim3(tp.nrows), dim3(TAIL_THREADS), dyn, tp));
   c->launches++;
   return OO_OK;
 }

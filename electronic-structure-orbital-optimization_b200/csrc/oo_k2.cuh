@@ -576,6 +576,7 @@ struct TailReduceParams {
   int accumulate;        // generic second pass: out += A, energy untouched
   int do_step;           // 1: run the optimiser transition in the last CTA; 2: its small-problem
                          // variant (M*N <= STEP_SMALL_MN)
+  int step_smem;         // the launch carries M*N doubles of dynamic shared memory for V
   StepParams step;
 };
 
@@ -690,8 +691,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_reduce(const TailReducePa
   if (p.do_step) {
     __threadfence();
     __syncthreads();
+    extern __shared__ double s_step_v[];      // M*N doubles when the launch reserved them
     if (small_step) opt_step_small_cta<TAIL_THREADS>(p.step, sm, ss);
-    else opt_step_cta<TAIL_THREADS>(p.step, sm);
+    else opt_step_cta<TAIL_THREADS>(p.step, sm, p.step_smem ? s_step_v : nullptr);
   }
 }
 

@@ -486,8 +486,11 @@ __device__ __forceinline__ StepDecision step_decide(const OptState& st, double f
 // One optimiser transition: consumes (f(U_k), G_k) and produces U_{k+1}, or raises the stop flag.
 // Called by every thread of ONE CTA of THREADS threads (the stand-alone k_step kernel, or the last
 // CTA of the tail kernel when the step is fused into the evaluation).
+// sV (optional): M*N doubles of shared memory for V = U_k - alpha G_k.  Without it the Gram matrix
+// and the final product read V through 4*M global loads per thread, which makes the one CTA
+// LSU-bound (~100 us cold at M=256, N=16); from shared memory they are conflict-free LDS.
 template <int THREADS>
-__device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
+__device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm, double* sV = nullptr) {
   OptState* st = p.st;
   if (st->done) return;
   const int tid = threadIdx.x, nth = THREADS;
@@ -522,14 +525,21 @@ __device__ inline void opt_step_cta(const StepParams& p, StepSmem& sm) {
     block_sum3(uu, ug, gg, sm.scratch3);
     alpha = (k & 1) ? uu / fabs(ug) : fabs(ug) / gg;
   }
-  // ---- shift histories; V = U_k - alpha G_k is formed on the fly from the shifted copies ------
+  // ---- shift histories; V = U_k - alpha G_k into shared memory when there is room, else formed
+  // on the fly from the shifted copies ------------------------------------------------------
   for (int i = tid; i < MN; i += nth) {
-    p.Uprev[i] = p.Ucur[i];
-    p.Gprev[i] = p.gE[i];
+    const double u = p.Ucur[i], g = p.gE[i];
+    p.Uprev[i] = u;
+    p.Gprev[i] = g;
+    if (sV) sV[i] = fma(-alpha, g, u);
   }
   __syncthreads();
-  retract_cta<THREADS>(p.Uprev, p.Gprev, alpha, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3,
-                       sm.cs, sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
+  if (sV)
+    retract_cta<THREADS>(sV, nullptr, 0.0, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3, sm.cs,
+                         sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
+  else
+    retract_cta<THREADS>(p.Uprev, p.Gprev, alpha, p.Ucur, p.M, p.N, sm.sA, sm.sB1, sm.sB2, sm.sB3,
+                         sm.cs, sm.scratch, &sm.sflag, &st->ns_iters, p.force_jacobi != 0);
   if (tid == 0) {
     st->alpha = alpha;
     st->P4[0] = dec.P0; st->P4[1] = dec.P1; st->P4[2] = dec.P2;
