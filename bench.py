@@ -67,14 +67,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_ms=25):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -83,9 +83,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """Median SM clock, throttle reasons and peak power of the samples taken inside `window`
+        (host time stamps (t0, t1) of the timed region; nvidia-smi is started long before it so
+        that it is already streaming), or of all samples."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,7 +99,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        picked = [ln for (ts, ln) in self.lines
+                  if window is None or window[0] <= ts <= window[1] + 0.5 * self.period_ms * 1e-3]
+        if window is not None and not picked and self.lines:      # region shorter than a period
+            mid = 0.5 * (window[0] + window[1])
+            picked = [min(self.lines, key=lambda tl: abs(tl[0] - mid))[1]]
+        for ln in picked:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -113,6 +121,21 @@ class ClockSampler:
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
                 "power_w_max": max(power) if power else None}
+
+
+def _window_clocks(sampler, window):
+    """Parse the samples of an already stopped sampler for another window."""
+    class _Done:                      # stop() terminates the process first: give it a finished one
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+        def kill(self):
+            pass
+    sampler.proc = _Done()
+    return sampler.stop(window)
 
 
 def _host_threads():
@@ -255,16 +278,18 @@ def timed_evals(eng, U_dev, K, W, stream, barrier, world, dev):
         eng.enqueue_energy_grad(U_dev[i % len(U_dev)])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.time()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for i in range(K):
             eng.enqueue_energy_grad(U_dev[(W + i) % len(U_dev)])
         ev1.record(stream)
     barrier()
+    t_host1 = time.time()
     tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    return float(tt.item())
+    return float(tt.item()), (t_host0, t_host1)
 
 
 def k1_timing(eng, U_dev, K, W, world, dev):
@@ -338,6 +363,11 @@ def main():
 
     M, N, K, W = args.M, args.N, args.steps, max(3, args.warmup)
     headline = (M, N) == (M_BENCH, N_BENCH)
+    # nvidia-smi takes a few hundred ms to deliver its first sample: start it now, filter its samples
+    # by the host time stamps of each timed region later
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # FP64 peaks of the idle GPU, before anything heats it up
     cold = esoo_b200.measure_peaks(local, 4 << 30) if rank == 0 else None
     eng, g, t0, mloc, ar_mode = build_engine(M, N, dev, rank, world, args, args.packed, args.dense)
@@ -371,15 +401,9 @@ def main():
             parity["ok"] = parity["dE_rel"] <= 1e-10 and parity["dgrad_rel"] <= 1e-9
 
     # ---------------- device-resident throughput (burst) ---------------------------------------
-    # nvidia-smi needs ~0.1 s to deliver its first sample: start it before the warm-up steps (same
-    # kernels, same load) so that short timed regions are still covered
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count()
-    ms_total = timed_evals(eng, U_dev, K, W, stream, barrier, world, dev)
+    ms_total, window = timed_evals(eng, U_dev, K, W, stream, barrier, world, dev)
     launches_per_eval = (eng.launch_count() - launches0) // (K + W)
-    clocks = sampler.stop() if rank == 0 else None
     value = K / (ms_total * 1e-3)
 
     # ---------------- per-kernel timing of the dominant kernel (CUDA events, same stream) -----
@@ -389,13 +413,10 @@ def main():
     sustained = None
     if not args.no_sustained:
         n_sus = max(K, int(2.2 / (ms_total * 1e-3 / K)))
-        s2 = ClockSampler(local)
-        if rank == 0:
-            s2.start()
-        ms_sus = timed_evals(eng, U_dev, n_sus, W, stream, barrier, world, dev)
-        c2 = s2.stop() if rank == 0 else None
+        ms_sus, window_sus = timed_evals(eng, U_dev, n_sus, W, stream, barrier, world, dev)
         sustained = {"value": n_sus / (ms_sus * 1e-3), "unit": "evals/s", "steps": n_sus,
-                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "clocks": c2}
+                     "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,
+                     "window": window_sus}
 
     # ---------------- end to end through host buffers (pipelined two deep) ---------------------
     for i in range(W):
@@ -453,7 +474,7 @@ def main():
             eng5.use_stream(stream)
             U5 = [synthetic.random_partial_unitary(M5, N5, seed=synthetic.SEED_U + i).to(dev)
                   for i in range(K5 + 3)]
-            ms5 = timed_evals(eng5, U5, K5, 3, stream, barrier, world, dev)
+            ms5, _w5 = timed_evals(eng5, U5, K5, 3, stream, barrier, world, dev)
             k1_5, k1_5_all, parts5 = k1_timing(eng5, U5, K5, 3, world, dev)
             slabs5 = eng5.streamed_slabs()
             b5 = 8.0 * slabs5 * M5 ** 2
@@ -474,6 +495,14 @@ def main():
         except Exception as exc:                  # the headline line must survive
             config5 = {"error": f"{type(exc).__name__}: {exc}"}
 
+    clocks = None
+    if rank == 0:
+        # one nvidia-smi stream for the whole run, cut by the host time stamps of the regions
+        clocks = sampler.stop(window)
+        if sustained is not None:
+            sustained["clocks"] = _window_clocks(sampler, sustained.pop("window"))
+    elif sustained is not None:
+        sustained.pop("window", None)
     if rank == 0:
         hbm_peak, peak_src = _load_peaks()
         dmma_cold, dfma_cold, read_cold = cold
