@@ -582,7 +582,16 @@ int enqueue_eval(oo_ctx* c, const double* U, double* out, const int* done_flag, 
   if (tm) CU_TRY(cudaEventRecord(c->ev[3], c->stream));
   if (nccl && (rc = do_allreduce(c, out, (size_t)c->M * c->N + 1))) return rc;
   if (step && !step_in_tail) {
-    k_step<<<1, K3_THREADS, 0, c->stream>>>(*step);
+    // separate transition launch (NCCL all-reduce, OO_NO_STEP_FUSION): V in dynamic shared memory
+    const size_t need = (size_t)c->M * c->N * sizeof(double);
+    static const bool smem_off = getenv("OO_NO_STEP_SMEM") != nullptr;
+    const bool in_smem = !smem_off && need <= (size_t)100 * 1024;
+    static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    if (in_smem && !attr_set[c->device & 7]) {
+      CU_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set[c->device & 7] = true;
+    }
+    k_step<<<1, K3_THREADS, in_smem ? need : 0, c->stream>>>(*step, in_smem ? 1 : 0);
     CU_TRY(cudaGetLastError());
     c->launches++;
   }

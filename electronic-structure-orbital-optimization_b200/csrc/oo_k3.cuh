@@ -624,9 +624,11 @@ __device__ inline void opt_step_small_cta(const StepParams& p, StepSmem& sm, Ste
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p) {
+// v_in_smem: the launch carries M*N doubles of dynamic shared memory for V (see opt_step_cta).
+__global__ void __launch_bounds__(K3_THREADS) k_step(const StepParams p, int v_in_smem) {
   __shared__ StepSmem sm;
-  opt_step_cta<K3_THREADS>(p, sm);
+  extern __shared__ double k_step_v[];
+  opt_step_cta<K3_THREADS>(p, sm, v_in_smem ? k_step_v : nullptr);
 }
 
 // Early stop requested by the host (a callback raised): behaves like the loop exit of the
